@@ -1,0 +1,249 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference functions.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+Every fixture stores the inputs and the reference's outputs, so the tests can
+replay them through (a) the oracle restatement on CPU and (b) the CUDA path on
+the GPU box, where /root/reference does not exist.  Seeds follow the reference's
+``cfg.RNG_SEED = 3`` (model/config.py:346).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+SEED = 3
+FORK_SCALES = [2, 4, 8, 16, 32]             # config.py:373
+FORK_RATIOS = [0.5, 0.75, 1, 1.25, 2]       # config.py:378
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def _detie(scores_flat):
+    """Make positive fg scores tie-free: bump duplicates by whole ulps."""
+    bits = scores_flat.clone().view(torch.int32)
+    for _ in range(64):
+        order = torch.argsort(bits, stable=True)
+        sb = bits[order]
+        dup = torch.zeros_like(sb, dtype=torch.bool)
+        dup[1:] = sb[1:] == sb[:-1]
+        if not dup.any():
+            break
+        bits[order[dup]] += 1
+    out = bits.view(torch.float32)
+    assert torch.unique(out).numel() == out.numel()
+    return out
+
+
+def synth_rpn(g, Hf, Wf, A):
+    """Synthetic RPN outputs per SURVEY §8d: softmax pair scores, small deltas."""
+    logits = torch.randn(1, Hf, Wf, 2 * A, generator=g)
+    pair = torch.stack((logits[..., :A], logits[..., A:]), dim=-1).softmax(-1)
+    prob = torch.cat((pair[..., 0], pair[..., 1]), dim=-1).contiguous()
+    fg = _detie(prob[..., A:].contiguous().view(-1))
+    prob[..., A:] = fg.view(1, Hf, Wf, A)
+    d = torch.randn(1, Hf, Wf, A, 4, generator=g)
+    d[..., :2] *= 0.1
+    d[..., 2:] *= 0.2
+    return prob, d.reshape(1, Hf, Wf, 4 * A).contiguous()
+
+
+def synth_gt_image(g, G, W, H, K):
+    wh = torch.exp(torch.rand(G, 2, generator=g) * (np.log(400.0) - np.log(16.0)) + np.log(16.0))
+    wh[:, 0].clamp_(max=W - 2)
+    wh[:, 1].clamp_(max=H - 2)
+    x1 = torch.rand(G, generator=g) * (W - 1 - wh[:, 0])
+    y1 = torch.rand(G, generator=g) * (H - 1 - wh[:, 1])
+    cls = torch.randint(1, K, (G,), generator=g).float()
+    return torch.stack((x1, y1, x1 + wh[:, 0], y1 + wh[:, 1], cls), dim=1)
+
+
+def main():
+    ref = ref_import.load()
+    cfg = ref.cfg
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+
+    # ---- anchors ------------------------------------------------------------------
+    kat9 = ref.ga.generate_anchors()
+    base25 = ref.ga.generate_anchors(ratios=np.array(FORK_RATIOS), scales=np.array(FORK_SCALES))
+    a_grid, a_len = ref.sn.generate_anchors_pre(6, 8, 16, FORK_SCALES, FORK_RATIOS, 1.0)
+    a_grid_s, _ = ref.sn.generate_anchors_pre(5, 7, 16, FORK_SCALES, FORK_RATIOS, 0.5)
+    cfg.NET_TYPE = "lidar"
+    n3, a3 = ref.g3.GridAnchor3dGenerator()._generate(5, 4, 16, cfg.LIDAR.ANCHOR_SCALES[0],
+                                                       cfg.LIDAR.ANCHOR_ANGLES, 1.0)
+    a3_aabb = ref.ub.bbaa_graphics_gems(a3.copy(), 4 * 16, 5 * 16, clip=False)
+    a3_aabb_clip = ref.ub.bbaa_graphics_gems(a3.copy(), 4 * 16, 5 * 16, clip=True)
+    dbg = np.array([[350, 400, 2, 50, 20, 3, np.pi / 8],            # tools/bbox_rot_debug.py:7
+                    [400, 300, 2, 50, 20, 3, np.pi / 8],
+                    [100, 100, 2, 50, 20, 3, np.pi / 8]], dtype=np.float64)
+    dbg_aabb = ref.ub.bbaa_graphics_gems(dbg.copy(), 700, 800)
+    g = torch.Generator().manual_seed(SEED)
+    rot_boxes = torch.rand(40, 7, generator=g) * torch.tensor([700, 800, 4, 60, 30, 3, np.pi]) \
+        - torch.tensor([0, 0, 0, -5, -5, -1, np.pi / 2])
+    rot_aabb_t = ref.ub.bbaa_graphics_gems_torch(rot_boxes.clone(), 700, 800, clip=True)
+    rot_aabb_t_nc = ref.ub.bbaa_graphics_gems_torch(rot_boxes.clone(), 700, 800, clip=False)
+    np.savez_compressed(os.path.join(OUT, "anchors.npz"), kat9=kat9, base25=base25, grid_6x8=a_grid,
+                        grid_len=a_len, grid_5x7_s05=a_grid_s, a3d_n=n3, a3d=a3, a3d_aabb=a3_aabb,
+                        a3d_aabb_clip=a3_aabb_clip, dbg=dbg, dbg_aabb=dbg_aabb, rot_boxes=_np(rot_boxes),
+                        rot_aabb_t=_np(rot_aabb_t), rot_aabb_t_nc=_np(rot_aabb_t_nc))
+
+    # ---- codecs + IoU ---------------------------------------------------------------
+    g = torch.Generator().manual_seed(SEED + 1)
+    ex = synth_gt_image(g, 64, 1920, 1280, 4)[:, :4]
+    gt = synth_gt_image(g, 64, 1920, 1280, 4)[:, :4]
+    enc = ref.bt.bbox_transform(ex, gt)
+    d1 = torch.randn(64, 4, generator=g) * torch.tensor([0.1, 0.1, 0.2, 0.2])
+    d3 = torch.randn(64, 12, generator=g) * 0.2
+    dec1 = ref.bt.bbox_transform_inv(ex, d1)
+    dec3 = ref.bt.bbox_transform_inv(ex, d3)
+    dec3_s = ref.bt.bbox_transform_inv(ex, d3, scales=1.5)
+    info_img = np.array([0, 1920, 0, 1280, 0, 0, 1.0], dtype=np.float32)
+    clip3 = ref.bt.clip_boxes(dec3 * 1.7 - 200, info_img)
+    qb = synth_gt_image(g, 9, 1920, 1280, 4)[:, :4]
+    iou = ref.ub.bbox_overlaps(ex, qb)
+    iou_np = ref.ub.bbox_overlaps(_np(ex).astype(np.float64), _np(qb).astype(np.float64))
+    a3d_e = torch.rand(64, 7, generator=g) * torch.tensor([700, 800, 4, 60, 30, 3, 3.0]) + \
+        torch.tensor([0, 0, 0.5, 5, 5, 1, -1.5])
+    gt7 = torch.rand(64, 7, generator=g) * torch.tensor([700, 800, 4, 60, 30, 3, 3.0]) + \
+        torch.tensor([0, 0, 0.5, 5, 5, 1, -1.5])
+    l_enc = ref.bt.lidar_3d_bbox_transform(ex, a3d_e, gt7)
+    d7 = torch.randn(64, 14, generator=g) * 0.2
+    l_dec = ref.bt.lidar_3d_bbox_transform_inv(ex, a3d_e.clone(), d7)
+    uc7 = torch.rand(64, 14, generator=g) * 0.3
+    l_uc = ref.bt.lidar_3d_uncertainty_transform_inv(ex, a3d_e.clone(), d7, uc7)
+    np.savez_compressed(os.path.join(OUT, "codecs.npz"), ex=_np(ex), gt=_np(gt), enc=_np(enc), d1=_np(d1),
+                        d3=_np(d3), dec1=_np(dec1), dec3=_np(dec3), dec3_s=_np(dec3_s), info=info_img,
+                        clip3=_np(clip3), qb=_np(qb), iou=_np(iou), iou_np64=iou_np, a3d=_np(a3d_e),
+                        gt7=_np(gt7), l_enc=_np(l_enc), d7=_np(d7), l_dec=_np(l_dec), uc7=_np(uc7),
+                        l_uc=_np(l_uc))
+
+    # ---- proposal_layer -------------------------------------------------------------
+    Hf, Wf, A = 20, 30, 25                     # 320x480 frame, N = 15000
+    info = np.array([0, Wf * 16, 0, Hf * 16, 0, 0, 1.0], dtype=np.float32)
+    anchors, _ = ref.sn.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)
+    anchors_t = torch.from_numpy(anchors)
+    a3_dummy = torch.arange(anchors.shape[0] * 7, dtype=torch.float32).view(-1, 7)
+    cfg.NET_TYPE = "image"
+    prop = {}
+    for key, pre, post in (("TEST", 3000, 150), ("TRAIN", 6000, 800)):
+        g = torch.Generator().manual_seed(SEED + 10 + len(prop))
+        prob, deltas = synth_rpn(g, Hf, Wf, A)
+        cfg[key].RPN_PRE_NMS_TOP_N = pre
+        cfg[key].RPN_POST_NMS_TOP_N = post
+        blob, sc, a3k = ref.pl.proposal_layer(prob, deltas, info, key, anchors_t, a3_dummy, A)
+        prop.update({f"{key}_prob": _np(prob), f"{key}_deltas": _np(deltas), f"{key}_pre": pre,
+                     f"{key}_post": post, f"{key}_blob": _np(blob), f"{key}_scores": _np(sc),
+                     f"{key}_a3d_col0": _np(a3k[:, 0])})
+    cfg.TEST.RPN_TOP_N = 500
+    tblob, tsc, tanc = ref.ptl.proposal_top_layer(prob, deltas, info, anchors_t, A)
+    prop.update(top_blob=_np(tblob), top_scores=_np(tsc), top_anchors=_np(tanc), top_n=500)
+    cfg.TEST.RPN_TOP_N = 5000
+    cfg.TRAIN.RPN_PRE_NMS_TOP_N, cfg.TRAIN.RPN_POST_NMS_TOP_N = 12000, 2000
+    cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N = 6000, 300
+    np.savez_compressed(os.path.join(OUT, "proposal.npz"), Hf=Hf, Wf=Wf, A=A, info=info, **prop)
+
+    # ---- anchor_target_layer_torch ---------------------------------------------------
+    g = torch.Generator().manual_seed(SEED + 20)
+    gtb = synth_gt_image(g, 12, Wf * 16, Hf * 16, 4)
+    gtb[:, 2:4] = torch.minimum(gtb[:, 2:4], torch.tensor([Wf * 16 - 1.0, Hf * 16 - 1.0]))
+    torch.manual_seed(SEED)
+    lab, tg, iw, ow = ref.atl.anchor_target_layer_torch(gtb, torch.zeros(0, 5), info, anchors_t, A, Hf, Wf,
+                                                         torch.device("cpu"))
+    np.savez_compressed(os.path.join(OUT, "anchor_target.npz"), Hf=Hf, Wf=Wf, A=A, info=info, gt=_np(gtb),
+                        seed=SEED, labels=_np(lab), targets=_np(tg), inside_w=_np(iw), outside_w=_np(ow))
+
+    # ---- proposal_target_layer (image strict; lidar strict) -----------------------------
+    g = torch.Generator().manual_seed(SEED + 30)
+    R = 400
+    jitter = torch.randn(R, 4, generator=g) * 6.0
+    rois = gtb[torch.randint(0, gtb.shape[0], (R,), generator=g), :4] + jitter
+    rois = torch.cat((rois[:200], synth_gt_image(g, 200, Wf * 16, Hf * 16, 4)[:, :4]), 0)
+    rois = torch.cat((torch.zeros(R, 1), rois), 1)
+    rsc = torch.rand(R, 1, generator=g)
+    a3r = torch.rand(R, 7, generator=g) * torch.tensor([480, 320, 4, 60, 30, 3, 3.0]) + \
+        torch.tensor([0, 0, 0.5, 5, 5, 1, -1.5])
+    tgt8 = torch.cat((torch.rand(gtb.shape[0], 7, generator=g) * torch.tensor([480, 320, 4, 60, 30, 3, 3.0])
+                      + torch.tensor([0, 0, 0.5, 5, 5, 1, -1.5]), gtb[:, 4:5]), 1)
+    pt = {}
+    for nt, E in (("image", 4), ("lidar", 7)):
+        cfg.NET_TYPE = nt
+        torch.manual_seed(SEED)
+        o = ref.prt.proposal_target_layer(rois, rsc, a3r, gtb, tgt8, torch.zeros(0, 5), 4, E)
+        for name, v in zip(("labels", "rois", "a3d", "scores", "targets", "inside_w", "outside_w"), o):
+            pt[f"{nt}_{name}"] = _np(v)
+    cfg.NET_TYPE = "image"
+    np.savez_compressed(os.path.join(OUT, "proposal_target.npz"), rois=_np(rois), scores=_np(rsc), a3d=_np(a3r),
+                        gt=_np(gtb), gt8=_np(tgt8), K=4, seed=SEED, **pt)
+
+    # ---- third-party kernels: NMS, RoIAlign fwd/bwd, FPN mapper ---------------------------
+    from torchvision.ops import nms as tv_nms, roi_align as tv_roi_align
+    g = torch.Generator().manual_seed(SEED + 40)
+    centers = torch.rand(60, 2, generator=g) * torch.tensor([400.0, 300.0])
+    nb = centers[torch.randint(0, 60, (1500,), generator=g)] + torch.randn(1500, 2, generator=g) * 6
+    nwh = torch.rand(1500, 2, generator=g) * 60 + 10
+    nboxes = torch.cat((nb - nwh / 2, nb + nwh / 2), 1)
+    nboxes[::97, 2:] = nboxes[::97, :2]                    # zero-area boxes (NaN IoU) survive
+    nscores = torch.rand(1500, generator=g).sort(descending=True)[0]
+    nms_out = {f"keep_{int(t * 100)}": _np(tv_nms(nboxes, nscores, t)) for t in (0.3, 0.5, 0.6, 0.7)}
+    C, H, W = 6, 24, 30
+    feat = torch.randn(1, C, H, W, generator=g)
+    rr = torch.rand(40, 4, generator=g) * torch.tensor([W * 16.0, H * 16.0, W * 8.0, H * 8.0])
+    rr = torch.stack((rr[:, 0], rr[:, 1], rr[:, 0] + rr[:, 2] + 1, rr[:, 1] + rr[:, 3] + 1), 1)
+    rr[0] = torch.tensor([-40.0, -30.0, 20.0, 25.0])         # partly outside
+    rr[1] = torch.tensor([W * 16 - 10.0, H * 16 - 10.0, W * 16 + 50.0, H * 16 + 40.0])
+    rr[2] = torch.tensor([100.0, 100.0, 100.0, 100.0])        # degenerate
+    rr[3] = torch.tensor([0.0, 0.0, W * 16.0 - 1, H * 16.0 - 1])  # whole frame
+    rrois = torch.cat((torch.zeros(40, 1), rr), 1)
+    ra = {}
+    for sr in (2, 0, 1):
+        f_ = feat.clone().requires_grad_(True)
+        o = tv_roi_align(f_, rrois, (7, 7), 1.0 / 16, sr, False)
+        go = torch.randn(o.shape, generator=torch.Generator().manual_seed(SEED + 41))
+        o.backward(go)
+        ra[f"out_s{sr}"] = _np(o)
+        ra[f"gin_s{sr}"] = _np(f_.grad)
+        ra[f"gout_s{sr}"] = _np(go)
+    ra["out_s2_aligned"] = _np(tv_roi_align(feat, rrois, (7, 7), 1.0 / 16, 2, True))
+    # FPN
+    feats = [torch.randn(1, 2, 128 // s, 192 // s, generator=g) for s in (1, 2, 4, 8)]   # strides 4..32 of 512x768
+    fsz = torch.exp(torch.rand(50, 2, generator=g) * (np.log(700.0) - np.log(20.0)) + np.log(20.0))
+    fsz[:, 1].clamp_(max=500.0)
+    fxy = torch.rand(50, 2, generator=g) * (torch.tensor([767.0, 511.0]) - fsz)
+    fb = torch.cat((fxy, fxy + fsz), 1)
+    from collections import OrderedDict
+    msra = ref.tp.MultiScaleRoIAlign(["p2", "p3", "p4", "p5"], 7, 2)
+    od = OrderedDict((n, ft) for n, ft in zip(["p2", "p3", "p4", "p5"], feats))
+    fout = msra(od, [fb], [(512, 768)])
+    flv = msra.map_levels([fb])
+    np.savez_compressed(os.path.join(OUT, "thirdparty.npz"), nms_boxes=_np(nboxes), nms_scores=_np(nscores),
+                        feat=_np(feat), rois=_np(rrois), fpn_boxes=_np(fb), fpn_out=_np(fout),
+                        fpn_levels=_np(flv), fpn_scales=np.array(msra.scales),
+                        **{f"fpn_feat{i}": _np(ft) for i, ft in enumerate(feats)}, **nms_out, **ra)
+
+    # ---- MC-dropout reductions -----------------------------------------------------------
+    g = torch.Generator().manual_seed(SEED + 50)
+    mu = torch.randn(1, 60, 14, generator=g) * 30
+    samp = mu + torch.randn(20, 60, 14, generator=g) * 0.05
+    var = ref.lu.compute_bbox_var(samp)
+    logits = torch.randn(20, 60, 4, generator=g)
+    import torch.nn.functional as F
+    ref.lu.F = F
+    mi = ref.lu.categorical_mutual_information(logits)
+    ent = ref.lu.categorical_entropy(torch.softmax(logits[0], dim=1))
+    np.savez_compressed(os.path.join(OUT, "uncertainty.npz"), samples=_np(samp), var=_np(var),
+                        logits=_np(logits), mutual_info=_np(mi), entropy=_np(ent))
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
