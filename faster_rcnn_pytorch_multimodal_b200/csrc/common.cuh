@@ -1,0 +1,75 @@
+// Shared helpers for the sm_100a detection-glue kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/b2d_glue.h"
+
+namespace b2d {
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr int kMaxSortElems = 16384;  // in-CTA bitonic capacity (128 KB of u64 keys)
+constexpr int kSelectBins = 65536;    // 16-bit first-level radix histogram
+
+extern std::atomic<uint64_t> g_launches;
+extern thread_local int tl_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+  tl_cuda_error = static_cast<int>(e);
+  return B2D_ERR_CUDA;
+}
+
+#define B2D_CUDA(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return ::b2d::cuda_fail(_e);  \
+  } while (0)
+
+// Call after every kernel launch: counts it and converts launch errors.
+#define B2D_LAUNCHED()                                   \
+  do {                                                   \
+    ::b2d::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    cudaError_t _e = cudaPeekAtLastError();              \
+    if (_e != cudaSuccess) return ::b2d::cuda_fail(_e);  \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ----- exact (non-contracted) fp32 arithmetic: the reference runs separate ATen ops, so
+// ----- every intermediate is rounded; nvcc would otherwise fuse a*b+c into one FMA.
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// torch.clamp(x, lo, hi) = min(max(x, lo), hi) with NaN propagated.
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  if (x != x) return x;
+  return fminf(fmaxf(x, lo), hi);
+}
+
+// Monotone map float -> uint32 (larger float => larger key); NaN sorts first in a
+// descending sort (torch.sort semantics), -0.0 == +0.0.
+__device__ __forceinline__ uint32_t score_key(float s) {
+  if (s != s) return 0xFFFFFFFFu;
+  uint32_t u = __float_as_uint(s + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// composite = key<<32 | ~index : descending composite == (score desc, index asc)
+__device__ __forceinline__ uint64_t composite_key(uint32_t key, uint32_t idx) {
+  return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ uint32_t composite_index(uint64_t c) {
+  return 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
+}
+
+// Largest float <= a double threshold: for float x, ((double)x > thr) <=> (x > floor_f(thr)).
+inline float float_floor_of(double thr) {
+  float f = static_cast<float>(thr);
+  if (static_cast<double>(f) > thr) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+}  // namespace b2d

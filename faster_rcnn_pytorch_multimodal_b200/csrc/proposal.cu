@@ -1,0 +1,496 @@
+// Proposal stage: fg-score select (2-level radix), in-CTA bitonic sort, decode + clip,
+// greedy NMS (nms.cu) and the post-NMS gather.
+//
+// Reference behaviour restated here: layer_utils/proposal_layer.py:18-57,
+// layer_utils/proposal_top_layer.py:18-59, model/bbox_transform.py:75-105,235-257.
+//
+// Data flow per frame (all launches cover every frame of the batch):
+//   1. score_hist_kernel      N fg scores -> 65536-bin histogram of the top 16 key bits
+//   2. score_threshold_kernel histogram -> threshold bin b* (smallest set of top bins holding >= k)
+//   3. score_compact_kernel   scores with bin >= b*  -> candidate composites (unordered)
+//   4. sort_decode_kernel     candidates -> exact top-k, sorted (score desc, index asc);
+//                             decodes + clips ONLY those k boxes (the reference decodes all N)
+//   5. nms_sorted_kernel      (nms.cu)
+//   6. proposal_gather_kernel kept positions -> rois / scores / anchors_3d rows
+#include "common.cuh"
+
+namespace b2d {
+
+int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, double thresh, int max_keep,
+                      int32_t* keep, int32_t* num_keep, cudaStream_t st);
+
+struct ProposalWs {
+  uint32_t* hist;         // [F][kSelectBins]
+  uint32_t* sel;          // [F][4]: thr_bin, n_cand (atomic), k, n_above
+  uint64_t* cand;         // [F][N]
+  float* sorted_boxes;    // [F][kmax][4]
+  float* sorted_scores;   // [F][kmax]
+  int32_t* sorted_index;  // [F][kmax]
+  int32_t* n_sorted;      // [F]
+  int32_t* keep;          // [F][max_out]
+  int32_t* num_keep;      // [F]
+  size_t bytes;
+};
+
+static int top_k_of(int N, int pre) { return (pre > 0 && pre < N) ? pre : N; }
+static int max_out_of(int N, int pre, int post) {
+  int k = top_k_of(N, pre);
+  return (post > 0 && post < k) ? post : k;
+}
+
+static ProposalWs carve(void* base, int F, int N, int pre, int post) {
+  ProposalWs w;
+  const int k = top_k_of(N, pre);
+  const int mo = max_out_of(N, pre, post);
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.hist = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)F * kSelectBins));
+  w.sel = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)F * 4));
+  w.cand = reinterpret_cast<uint64_t*>(take(sizeof(uint64_t) * (size_t)F * N));
+  w.sorted_boxes = reinterpret_cast<float*>(take(sizeof(float) * (size_t)F * k * 4));
+  w.sorted_scores = reinterpret_cast<float*>(take(sizeof(float) * (size_t)F * k));
+  w.sorted_index = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * k));
+  w.n_sorted = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
+  w.keep = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * mo));
+  w.num_keep = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float fg_score(const float* __restrict__ cls_prob, int f, int n_loc, int A, int n) {
+  const int l = n / A;
+  const int a = n - l * A;
+  return __ldg(cls_prob + ((size_t)f * n_loc + l) * (2 * A) + A + a);
+}
+
+__global__ void __launch_bounds__(256) score_hist_kernel(const float* __restrict__ cls_prob, int n_loc, int A,
+                                                         int N, uint32_t* __restrict__ hist) {
+  const int f = blockIdx.y;
+  uint32_t* h = hist + (size_t)f * kSelectBins;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const uint32_t key = score_key(fg_score(cls_prob, f, n_loc, A, n));
+    atomicAdd(h + (key >> 16), 1u);
+  }
+}
+
+// One CTA per frame: find the smallest set of top bins holding at least k scores.
+__global__ void __launch_bounds__(1024) score_threshold_kernel(const uint32_t* __restrict__ hist,
+                                                               uint32_t* __restrict__ sel, int k) {
+  __shared__ uint32_t part[1024];
+  const int f = blockIdx.x;
+  const int t = threadIdx.x;
+  const uint32_t* h = hist + (size_t)f * kSelectBins;
+  constexpr int kPer = kSelectBins / 1024;
+  uint32_t local = 0;
+#pragma unroll 8
+  for (int b = 0; b < kPer; ++b) local += h[t * kPer + b];
+  part[t] = local;
+  __syncthreads();
+  // suffix sum over threads (inclusive), Hillis-Steele on 1024 entries
+  for (int d = 1; d < 1024; d <<= 1) {
+    uint32_t v = (t + d < 1024) ? part[t + d] : 0u;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  const uint32_t incl = part[t];           // scores in bins >= t*kPer
+  const uint32_t above = incl - local;     // scores in bins owned by higher threads
+  if (t == 0) {
+    sel[f * 4 + 1] = 0u;
+    sel[f * 4 + 2] = (uint32_t)k;
+  }
+  if (k > 0 && above < (uint32_t)k && incl >= (uint32_t)k) {
+    uint32_t cum = above;
+    for (int b = kPer - 1; b >= 0; --b) {
+      const uint32_t c = h[t * kPer + b];
+      if (cum + c >= (uint32_t)k) {
+        sel[f * 4 + 0] = (uint32_t)(t * kPer + b);
+        sel[f * 4 + 3] = cum;
+        break;
+      }
+      cum += c;
+    }
+  }
+  if (k <= 0 && t == 0) {
+    sel[f * 4 + 0] = kSelectBins;  // nothing selected
+    sel[f * 4 + 3] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) score_compact_kernel(const float* __restrict__ cls_prob, int n_loc, int A,
+                                                            int N, uint32_t* __restrict__ sel,
+                                                            uint64_t* __restrict__ cand) {
+  const int f = blockIdx.y;
+  const uint32_t thr_bin = sel[f * 4 + 0];
+  uint32_t* counter = sel + f * 4 + 1;
+  uint64_t* out = cand + (size_t)f * N;
+  const int stride = gridDim.x * blockDim.x;
+  const int n_iter = (N + stride - 1) / stride;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int it = 0; it < n_iter; ++it, n += stride) {
+    bool take = false;
+    uint32_t key = 0;
+    if (n < N) {
+      key = score_key(fg_score(cls_prob, f, n_loc, A, n));
+      take = (key >> 16) >= thr_bin;
+    }
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, take);
+    if (ballot) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(ballot) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(ballot));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (take) out[base + __popc(ballot & ((1u << lane) - 1u))] = composite_key(key, (uint32_t)n);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// In-CTA exact top-k + sort.  Dynamic smem: n_pad u64 keys (<= kMaxSortElems).
+__device__ void bitonic_sort_desc(uint64_t* s, int n_pad) {
+  const int half = n_pad >> 1;
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = threadIdx.x; p < half; p += blockDim.x) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int q = i | j;
+        const uint64_t a = s[i], b = s[q];
+        const bool desc = (i & k) == 0;  // descending runs first => final order descending
+        if ((a < b) == desc) {
+          s[i] = b;
+          s[q] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Slow path (more than kMaxSortElems candidates, e.g. massive score ties): exact MSB radix
+// select of the k-th largest composite over the global candidate list; returns it.
+__device__ uint64_t radix_select_kth(const uint64_t* __restrict__ cand, int m, int k, uint32_t* hist256,
+                                     uint64_t* bcast) {
+  uint64_t prefix = 0, mask = 0;
+  int k_rem = k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist256[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint64_t c = cand[i];
+      if ((c & mask) == prefix) atomicAdd(&hist256[(c >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, d = 255;
+      for (; d > 0; --d) {
+        if (cum + (int)hist256[d] >= k_rem) break;
+        cum += (int)hist256[d];
+      }
+      bcast[0] = (uint64_t)d;
+      bcast[1] = (uint64_t)cum;
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 0xFFull << shift;
+    k_rem -= (int)bcast[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+struct DecodeArgs {
+  const float* cls_prob;
+  const float* bbox_pred;
+  const float* info;     // [F][7]
+  const float* anchors;  // [N][4]
+  int n_loc, A, N;
+};
+
+__device__ __forceinline__ void decode_clip(const float* __restrict__ anc, const float* __restrict__ d,
+                                            const float* __restrict__ info, float out[4]) {
+  // bbox_transform_inv (bbox_transform.py:82-103) then clip_boxes (:252-255); every op rounded.
+  const float x1 = anc[0], y1 = anc[1], x2 = anc[2], y2 = anc[3];
+  const float w = fadd(fsub(x2, x1), 1.0f);
+  const float h = fadd(fsub(y2, y1), 1.0f);
+  const float diag = __fsqrt_rn(fadd(fmul(w, w), fmul(h, h)));
+  const float cx = fadd(x1, fmul(0.5f, w));
+  const float cy = fadd(y1, fmul(0.5f, h));
+  const float pcx = fadd(fmul(d[0], diag), cx);
+  const float pcy = fadd(fmul(d[1], diag), cy);
+  const float pw = fmul(expf(d[2]), w);
+  const float ph = fmul(expf(d[3]), h);
+  const float hx = fmul(0.5f, pw), hy = fmul(0.5f, ph);
+  const float xlo = info[0], xhi = fsub(info[1], 1.0f), ylo = info[2], yhi = fsub(info[3], 1.0f);
+  out[0] = clampf(fsub(pcx, hx), xlo, xhi);
+  out[1] = clampf(fsub(pcy, hy), ylo, yhi);
+  out[2] = clampf(fadd(pcx, hx), xlo, xhi);
+  out[3] = clampf(fadd(pcy, hy), ylo, yhi);
+}
+
+__global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a, const uint32_t* __restrict__ sel,
+                                                           const uint64_t* __restrict__ cand_all,
+                                                           float* __restrict__ sorted_boxes,
+                                                           float* __restrict__ sorted_scores,
+                                                           int32_t* __restrict__ sorted_index,
+                                                           int32_t* __restrict__ n_sorted, int k_cap,
+                                                           int decode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ uint32_t hist256[256];
+  __shared__ uint64_t bcast[2];
+  __shared__ int s_count;
+
+  const int f = blockIdx.x;
+  const int m = (int)sel[f * 4 + 1];
+  const int k = min((int)sel[f * 4 + 2], m);
+  const uint64_t* cand = cand_all + (size_t)f * a.N;
+
+  int cnt;
+  if (m <= kMaxSortElems) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) keys[i] = cand[i];
+    cnt = m;
+  } else {
+    const uint64_t kth = radix_select_kth(cand, m, k, hist256, bcast);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint64_t c = cand[i];
+      if (c >= kth) keys[atomicAdd(&s_count, 1)] = c;  // composites are unique: exactly k survive
+    }
+    __syncthreads();
+    cnt = s_count;
+  }
+  int n_pad = 2;
+  while (n_pad < cnt) n_pad <<= 1;
+  for (int i = cnt + threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = 0ull;  // below every real key
+  __syncthreads();
+  bitonic_sort_desc(keys, n_pad);
+
+  if (threadIdx.x == 0) n_sorted[f] = k;
+  float* ob = sorted_boxes + (size_t)f * k_cap * 4;
+  float* os = sorted_scores + (size_t)f * k_cap;
+  int32_t* oi = sorted_index + (size_t)f * k_cap;
+  const float* info = a.info + f * 7;
+  for (int i = threadIdx.x; i < k_cap; i += blockDim.x) {
+    float box[4] = {0.f, 0.f, 0.f, 0.f};
+    float sc = 0.f;
+    int idx = 0;
+    if (i < k) {
+      idx = (int)composite_index(keys[i]);
+      sc = fg_score(a.cls_prob, f, a.n_loc, a.A, idx);
+      if (decode) {
+        const float* anc = a.anchors + (size_t)idx * 4;
+        const float* d = a.bbox_pred + ((size_t)f * a.N + idx) * 4;
+        const float an[4] = {__ldg(anc), __ldg(anc + 1), __ldg(anc + 2), __ldg(anc + 3)};
+        const float dd[4] = {__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3)};
+        decode_clip(an, dd, info, box);
+      }
+    }
+    ob[i * 4 + 0] = box[0];
+    ob[i * 4 + 1] = box[1];
+    ob[i * 4 + 2] = box[2];
+    ob[i * 4 + 3] = box[3];
+    os[i] = sc;
+    oi[i] = idx;
+  }
+}
+
+// keep positions -> output rows (proposal_layer.py:48-55); pads the tail with zeros.
+__global__ void __launch_bounds__(256) proposal_gather_kernel(
+    const float* __restrict__ sorted_boxes, const float* __restrict__ sorted_scores,
+    const int32_t* __restrict__ sorted_index, const int32_t* __restrict__ keep,
+    const int32_t* __restrict__ num_keep, const float* __restrict__ anchors_3d, int k_cap, int max_out,
+    int batch_index_stride, float* __restrict__ rois, float* __restrict__ roi_scores,
+    float* __restrict__ roi_a3d, int32_t* __restrict__ roi_anchor, int32_t* __restrict__ num_out) {
+  const int f = blockIdx.y;
+  const int nk = num_keep[f];
+  if (blockIdx.x == 0 && threadIdx.x == 0) num_out[f] = nk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max_out; i += gridDim.x * blockDim.x) {
+    float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float sc = 0.f;
+    int idx = -1;
+    if (i < nk) {
+      const int p = keep[(size_t)f * max_out + i];
+      const float* b = sorted_boxes + ((size_t)f * k_cap + p) * 4;
+      r[0] = (float)(f * batch_index_stride);
+      r[1] = b[0];
+      r[2] = b[1];
+      r[3] = b[2];
+      r[4] = b[3];
+      sc = sorted_scores[(size_t)f * k_cap + p];
+      idx = sorted_index[(size_t)f * k_cap + p];
+    }
+    float* o = rois + ((size_t)f * max_out + i) * 5;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) o[c] = r[c];
+    roi_scores[(size_t)f * max_out + i] = sc;
+    if (roi_anchor) roi_anchor[(size_t)f * max_out + i] = idx;
+    if (roi_a3d) {
+      float* o3 = roi_a3d + ((size_t)f * max_out + i) * 7;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) o3[c] = (idx >= 0 && anchors_3d) ? __ldg(anchors_3d + (size_t)idx * 7 + c) : 0.f;
+    }
+  }
+}
+
+// proposal_top_layer output rows: rois + scores + the selected anchors.
+__global__ void __launch_bounds__(256) proposal_top_gather_kernel(
+    const float* __restrict__ sorted_boxes, const float* __restrict__ sorted_scores,
+    const int32_t* __restrict__ sorted_index, const float* __restrict__ anchors, int top_n,
+    int batch_index_stride, float* __restrict__ rois, float* __restrict__ roi_scores,
+    float* __restrict__ roi_anchors) {
+  const int f = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < top_n; i += gridDim.x * blockDim.x) {
+    const float* b = sorted_boxes + ((size_t)f * top_n + i) * 4;
+    float* o = rois + ((size_t)f * top_n + i) * 5;
+    o[0] = (float)(f * batch_index_stride);
+    o[1] = b[0];
+    o[2] = b[1];
+    o[3] = b[2];
+    o[4] = b[3];
+    roi_scores[(size_t)f * top_n + i] = sorted_scores[(size_t)f * top_n + i];
+    const int idx = sorted_index[(size_t)f * top_n + i];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) roi_anchors[((size_t)f * top_n + i) * 4 + c] = __ldg(anchors + (size_t)idx * 4 + c);
+  }
+}
+
+__global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restrict__ scores, int n,
+                                                            int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int f = blockIdx.x;
+  int n_pad = 2;
+  while (n_pad < n) n_pad <<= 1;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    keys[i] = i < n ? composite_key(score_key(scores[(size_t)f * n + i]), (uint32_t)i) : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(keys, n_pad);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[(size_t)f * n + i] = (int32_t)composite_index(keys[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+static int select_sort(int F, int n_loc, int A, const float* cls_prob, const float* bbox_pred, const float* info,
+                       const float* anchors, int k, int decode, const ProposalWs& w, cudaStream_t st) {
+  const int N = n_loc * A;
+  B2D_CUDA(cudaMemsetAsync(w.hist, 0, sizeof(uint32_t) * (size_t)F * kSelectBins, st));
+  int gx = ceil_div(N, 256 * 4);
+  if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, F);
+  score_hist_kernel<<<grid, 256, 0, st>>>(cls_prob, n_loc, A, N, w.hist);
+  B2D_LAUNCHED();
+  score_threshold_kernel<<<F, 1024, 0, st>>>(w.hist, w.sel, k);
+  B2D_LAUNCHED();
+  score_compact_kernel<<<grid, 256, 0, st>>>(cls_prob, n_loc, A, N, w.sel, w.cand);
+  B2D_LAUNCHED();
+  const size_t smem = sizeof(uint64_t) * kMaxSortElems;
+  B2D_CUDA(cudaFuncSetAttribute(sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DecodeArgs a{cls_prob, bbox_pred, info, anchors, n_loc, A, N};
+  sort_decode_kernel<<<F, 1024, smem, st>>>(a, w.sel, w.cand, w.sorted_boxes, w.sorted_scores, w.sorted_index,
+                                            w.n_sorted, k, decode);
+  B2D_LAUNCHED();
+  return B2D_OK;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" size_t b2d_proposal_workspace_bytes(int num_frames, int n_loc, int num_anchors, int pre_nms,
+                                               int post_nms) {
+  if (num_frames <= 0 || n_loc <= 0 || num_anchors <= 0) return 0;
+  return carve(nullptr, num_frames, n_loc * num_anchors, pre_nms, post_nms).bytes;
+}
+
+extern "C" int b2d_max_pre_nms(void) { return kMaxSortElems; }
+
+extern "C" int b2d_proposal(int F, int n_loc, int A, const float* cls_prob, const float* bbox_pred,
+                            const float* info, const float* anchors, const float* anchors_3d, int pre_nms,
+                            int post_nms, double nms_thresh, int batch_index_stride, float* rois,
+                            float* roi_scores, float* roi_a3d, int32_t* roi_anchor, int32_t* num_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (F <= 0 || n_loc <= 0 || A <= 0 || !cls_prob || !bbox_pred || !info || !anchors || !rois || !roi_scores ||
+      !num_out)
+    return B2D_ERR_INVALID_ARG;
+  if ((long long)n_loc * A > 0x7FFFFFFFll / 8) return B2D_ERR_UNSUPPORTED;
+  const int N = n_loc * A;
+  const int k = top_k_of(N, pre_nms);
+  if (k > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
+  const int mo = max_out_of(N, pre_nms, post_nms);
+  ProposalWs w = carve(workspace, F, N, pre_nms, post_nms);
+  if (!workspace || workspace_bytes < w.bytes) return B2D_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  int rc = select_sort(F, n_loc, A, cls_prob, bbox_pred, info, anchors, k, 1, w, st);
+  if (rc != B2D_OK) return rc;
+  rc = launch_nms_sorted(F, k, w.sorted_boxes, w.n_sorted, nms_thresh, mo, w.keep, w.num_keep, st);
+  if (rc != B2D_OK) return rc;
+  dim3 grid(ceil_div(mo, 256), F);
+  proposal_gather_kernel<<<grid, 256, 0, st>>>(w.sorted_boxes, w.sorted_scores, w.sorted_index, w.keep, w.num_keep,
+                                               anchors_3d, k, mo, batch_index_stride, rois, roi_scores, roi_a3d,
+                                               roi_anchor, num_out);
+  B2D_LAUNCHED();
+  return B2D_OK;
+}
+
+extern "C" int b2d_proposal_top(int F, int n_loc, int A, const float* cls_prob, const float* bbox_pred,
+                                const float* info, const float* anchors, int top_n, int batch_index_stride,
+                                float* rois, float* roi_scores, float* roi_anchors, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (F <= 0 || n_loc <= 0 || A <= 0 || !cls_prob || !bbox_pred || !info || !anchors || !rois || !roi_scores ||
+      !roi_anchors || top_n <= 0)
+    return B2D_ERR_INVALID_ARG;
+  const int N = n_loc * A;
+  if (top_n > N) return B2D_ERR_UNSUPPORTED;  // the reference's random-fill branch stays on the host
+  if (top_n > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
+  ProposalWs w = carve(workspace, F, N, top_n, top_n);
+  if (!workspace || workspace_bytes < w.bytes) return B2D_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  int rc = select_sort(F, n_loc, A, cls_prob, bbox_pred, info, anchors, top_n, 1, w, st);
+  if (rc != B2D_OK) return rc;
+  dim3 grid(ceil_div(top_n, 256), F);
+  proposal_top_gather_kernel<<<grid, 256, 0, st>>>(w.sorted_boxes, w.sorted_scores, w.sorted_index, anchors, top_n,
+                                                   batch_index_stride, rois, roi_scores, roi_anchors);
+  B2D_LAUNCHED();
+  return B2D_OK;
+}
+
+extern "C" int b2d_proposal_debug_sorted(int F, int n_loc, int A, int pre_nms, int post_nms, const void* workspace,
+                                         float* sorted_boxes, float* sorted_scores, int32_t* sorted_index,
+                                         void* stream) {
+  if (!workspace || F <= 0) return B2D_ERR_INVALID_ARG;
+  const int N = n_loc * A;
+  const int k = top_k_of(N, pre_nms);
+  ProposalWs w = carve(const_cast<void*>(workspace), F, N, pre_nms, post_nms);
+  cudaStream_t st = as_stream(stream);
+  if (sorted_boxes)
+    B2D_CUDA(cudaMemcpyAsync(sorted_boxes, w.sorted_boxes, sizeof(float) * (size_t)F * k * 4,
+                             cudaMemcpyDeviceToDevice, st));
+  if (sorted_scores)
+    B2D_CUDA(cudaMemcpyAsync(sorted_scores, w.sorted_scores, sizeof(float) * (size_t)F * k,
+                             cudaMemcpyDeviceToDevice, st));
+  if (sorted_index)
+    B2D_CUDA(cudaMemcpyAsync(sorted_index, w.sorted_index, sizeof(int32_t) * (size_t)F * k,
+                             cudaMemcpyDeviceToDevice, st));
+  return B2D_OK;
+}
+
+extern "C" int b2d_argsort_desc(int F, int n, const float* scores, int32_t* order, void* stream) {
+  if (F <= 0 || n < 0 || !scores || !order) return B2D_ERR_INVALID_ARG;
+  if (n == 0) return B2D_OK;
+  if (n > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
+  const size_t smem = sizeof(uint64_t) * kMaxSortElems;
+  B2D_CUDA(cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n_pad = 2;
+  while (n_pad < n) n_pad <<= 1;
+  argsort_desc_kernel<<<F, 1024, sizeof(uint64_t) * n_pad, as_stream(stream)>>>(scores, n, order);
+  B2D_LAUNCHED();
+  return B2D_OK;
+}

@@ -1,0 +1,97 @@
+"""LevelMapper / MultiScaleRoIAlign with the reference's interface (lib/utils/torchpoolers.py).
+
+The per-level nonzero / gather / roi_align / scatter loop (:187-199) becomes: one level-map
+kernel, then one RoIAlign launch per level that reads its RoIs through an index list and writes
+straight into the shared output (no gather, no scatter, no per-level sync).
+"""
+from typing import Dict, List, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class LevelMapper(object):
+    """FPN eq.(1) (torchpoolers.py:20-51)."""
+
+    def __init__(self, k_min, k_max, canonical_scale=224, canonical_level=4, eps=1e-6):
+        self.k_min, self.k_max = k_min, k_max
+        self.s0, self.lvl0, self.eps = canonical_scale, canonical_level, eps
+
+    def __call__(self, boxlists):
+        return ops.fpn_level_map(torch.cat(list(boxlists), dim=0), self.k_min, self.k_max, self.s0, self.lvl0,
+                                 self.eps)
+
+
+def initLevelMapper(k_min, k_max, canonical_scale=224, canonical_level=4, eps=1e-6):
+    return LevelMapper(k_min, k_max, canonical_scale, canonical_level, eps)
+
+
+class MultiScaleRoIAlign(nn.Module):
+    """torchpoolers.py:54-200."""
+
+    def __init__(self, featmap_names, output_size, sampling_ratio):
+        super().__init__()
+        if isinstance(output_size, int):
+            output_size = (output_size, output_size)
+        self.featmap_names = featmap_names
+        self.sampling_ratio = sampling_ratio
+        self.output_size = tuple(output_size)
+        self.scales = None
+        self.map_levels = None
+
+    def convert_to_roi_format(self, boxes):
+        ids = torch.cat([torch.full_like(b[:, :1], i) for i, b in enumerate(boxes)], dim=0)
+        return torch.cat([ids, torch.cat(boxes, dim=0)], dim=1)
+
+    def infer_scale(self, feature, original_size):
+        possible = []
+        for s1, s2 in zip(feature.shape[-2:], original_size):                     # :107-117
+            possible.append(2 ** float(torch.tensor(float(s1) / float(s2)).log2().round()))
+        assert possible[0] == possible[1]
+        return possible[0]
+
+    def setup_scales(self, features, image_shapes):
+        assert len(image_shapes) != 0
+        original = (max(s[0] for s in image_shapes), max(s[1] for s in image_shapes))
+        scales = [self.infer_scale(f, original) for f in features]
+        lvl_min = -torch.log2(torch.tensor(scales[0], dtype=torch.float32)).item()
+        lvl_max = -torch.log2(torch.tensor(scales[-1], dtype=torch.float32)).item()
+        self.scales = scales
+        self.map_levels = initLevelMapper(int(lvl_min), int(lvl_max))
+
+    def forward(self, x: Dict[str, torch.Tensor], boxes: List[torch.Tensor], image_shapes: List[Tuple[int, int]]):
+        feats = [v for k, v in x.items() if k in self.featmap_names]
+        rois = self.convert_to_roi_format(boxes)
+        if self.scales is None:
+            self.setup_scales(feats, image_shapes)
+        if len(feats) == 1:
+            return ops.roi_align(feats[0], rois, self.output_size, self.scales[0], self.sampling_ratio)
+        levels = self.map_levels(boxes)
+        return _MultiLevelFn.apply(rois, levels, self.output_size, tuple(self.scales), self.sampling_ratio, *feats)
+
+
+class _MultiLevelFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, levels, out_hw, scales, sampling_ratio, *feats):
+        rois_c = ops.f32c(rois)
+        R, C = rois_c.shape[0], feats[0].shape[1]
+        out = torch.zeros((R, C) + tuple(out_hw), device=feats[0].device)
+        id_lists = []
+        for lvl, (f, s) in enumerate(zip(feats, scales)):
+            ids = (levels == lvl).nonzero().view(-1).to(torch.int32).contiguous()   # device-side, no sync
+            id_lists.append(ids)
+            ops._roi_align_forward(ops.f32c(f), rois_c, out_hw, s, sampling_ratio, False, roi_ids=ids, out=out)
+        ctx.save_for_backward(rois_c, *id_lists)
+        ctx.meta = (out_hw, scales, sampling_ratio, [tuple(f.shape) for f in feats])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rois_c, *id_lists = ctx.saved_tensors
+        out_hw, scales, sr, shapes = ctx.meta
+        g = ops.f32c(grad_out)
+        grads = [ops._roi_align_backward(g, rois_c, shp, out_hw, s, sr, False, roi_ids=ids)
+                 for shp, s, ids in zip(shapes, scales, id_lists)]
+        return (None, None, None, None, None) + tuple(grads)
