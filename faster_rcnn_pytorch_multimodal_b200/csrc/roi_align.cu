@@ -19,104 +19,14 @@
 // one thread per channel.  A thread is the only writer of its channel plane, RoIs are
 // visited in index order, so accumulation is deterministic with no atomics at all; each
 // grad_feat element is written to HBM exactly once.
-#include "common.cuh"
+#include "roi_common.cuh"
 
 namespace b2d {
 
-struct RoiGeom {
-  float start_w, start_h, bin_w, bin_h;
-  int grid_w, grid_h;
-  float count;
-};
-
-__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, float scale, int PH, int PW,
-                                                int sampling_ratio, bool aligned) {
-  RoiGeom g;
-  const float off = aligned ? 0.5f : 0.0f;
-  g.start_w = fsub(fmul(roi[1], scale), off);
-  g.start_h = fsub(fmul(roi[2], scale), off);
-  const float end_w = fsub(fmul(roi[3], scale), off);
-  const float end_h = fsub(fmul(roi[4], scale), off);
-  float rw = fsub(end_w, g.start_w);
-  float rh = fsub(end_h, g.start_h);
-  if (!aligned) {
-    rw = fmaxf(rw, 1.0f);
-    rh = fmaxf(rh, 1.0f);
-  }
-  g.bin_h = fdiv(rh, (float)PH);
-  g.bin_w = fdiv(rw, (float)PW);
-  g.grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(fdiv(rh, (float)PH));
-  g.grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(fdiv(rw, (float)PW));
-  g.count = (float)max(g.grid_h * g.grid_w, 1);
-  return g;
-}
-
-struct AxisTap {
-  int lo, hi;     // pixel indices
-  float wlo, whi; // weights of lo / hi (hy, ly in torchvision's naming)
-  bool ok;
-};
-
-__device__ __forceinline__ AxisTap axis_tap(float start, float bin, int p, int i, int grid, int limit) {
-  AxisTap t;
-  float c = fadd(fadd(start, fmul((float)p, bin)), fdiv(fmul(fadd((float)i, 0.5f), bin), (float)grid));
-  t.ok = !(c < -1.0f || c > (float)limit);
-  if (c <= 0.0f) c = 0.0f;
-  int lo = (int)c;
-  int hi;
-  if (lo >= limit - 1) {
-    hi = lo = limit - 1;
-    c = (float)lo;
-  } else {
-    hi = lo + 1;
-  }
-  const float l = fsub(c, (float)lo);
-  t.lo = lo;
-  t.hi = hi;
-  t.whi = l;
-  t.wlo = fsub(1.0f, l);
-  if (!t.ok) {
-    t.lo = t.hi = 0;
-    t.wlo = t.whi = 0.0f;
-  }
-  return t;
-}
-
-struct RoiList {
-  const float* rois;        // [R,5]
-  const int32_t* ids;       // optional indirection
-  int n;                    // list length (R or n_ids)
-  const int32_t* seg_count; // optional [F]: frame f owns list entries [f*seg_stride, +seg_count[f])
-  int seg_stride;
-};
-
-// ------------------------------------------------------------------------------------------
-// mbarrier + 1-D bulk TMA helpers (sm_90+/sm_100a PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+size_t sweep_workspace_bytes(int F, int H, int n_list);
+int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
+                            float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
+                            cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 template <int CPB>
@@ -370,18 +280,27 @@ static int launch_fwd_planes(int F, int C, int H, int W, const float* feat, cons
 
 using namespace b2d;
 
-extern "C" size_t b2d_roi_align_workspace_bytes(int, int, int, int, int) { return 0; }
+extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W*/, int num_rois) {
+  if (F <= 0 || H <= 0 || num_rois <= 0) return 0;
+  return sweep_workspace_bytes(F, H, num_rois);
+}
 
 extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
                                      const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
                                      int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, float* out,
-                                     void* /*workspace*/, size_t /*workspace_bytes*/, void* stream) {
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   if (F <= 0 || C <= 0 || H <= 0 || W <= 0 || PH <= 0 || PW <= 0 || !feat || !out) return B2D_ERR_INVALID_ARG;
   RoiList L{rois, roi_ids, roi_ids ? n_roi_ids : num_rois, seg_count, seg_stride};
   if (seg_count && (seg_stride <= 0 || (long long)seg_stride * F > L.n)) return B2D_ERR_INVALID_ARG;
   if (L.n <= 0) return B2D_OK;
   if (!rois) return B2D_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  // production path: channel-on-lanes sweep kernel (roi_align_sweep.cu); needs the workspace
+  if (C >= 16) {
+    const int rc = roi_align_forward_sweep(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
+                                           workspace, workspace_bytes, st);
+    if (rc != B2D_ERR_UNSUPPORTED) return rc;
+  }
   const size_t plane = (size_t)H * W * sizeof(float);
   int cpb = (int)(fwd_smem_budget() / plane);
   if (cpb > 8) cpb = 8;

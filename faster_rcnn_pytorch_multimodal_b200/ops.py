@@ -152,9 +152,11 @@ def _roi_align_forward(feat, rois, out_hw, scale, sampling_ratio, aligned, roi_i
     if R == 0 or (roi_ids is not None and roi_ids.numel() == 0):
         return out
     n_ids = 0 if roi_ids is None else roi_ids.numel()
-    check(lib().b2d_roi_align_forward(Fr, Cc, H, W, ptr(feat), ptr(rois), R, ptr(roi_ids), n_ids, ptr(seg_count),
-                                      int(seg_stride), out_hw[0], out_hw[1], float(scale), int(sampling_ratio),
-                                      int(bool(aligned)), ptr(out), None, 0, stream_ptr(feat.device)),
+    L = lib()
+    ws = workspaces.get(feat.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, max(R, n_ids)))
+    check(L.b2d_roi_align_forward(Fr, Cc, H, W, ptr(feat), ptr(rois), R, ptr(roi_ids), n_ids, ptr(seg_count),
+                                  int(seg_stride), out_hw[0], out_hw[1], float(scale), int(sampling_ratio),
+                                  int(bool(aligned)), ptr(out), ptr(ws), ws.numel(), stream_ptr(feat.device)),
           "b2d_roi_align_forward")
     return out
 
