@@ -292,7 +292,8 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))            # one ncu --set full capture, scaled to this run's frames per launch
+            traffic = tj["dram_bytes_per_launch"] * F / tj["frames_in_launch"]
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -303,7 +304,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({F * (b_prop + cfg['C'] * n_loc * 4) / 1e6:.0f} MB read, "
                                     f"{F * M * cfg['C'] * P * P * 4 / 1e6:.0f} MB written per step)",
                        "parallelism": f"frame-stream x{world}, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "roi_align_fwd_planes_kernel", "achieved": crop_gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "roi_align_fwd_sweep7_kernel", "achieved": crop_gbs, "peak": peak,
                          "unit": "GB/s", "frac": crop_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": F * b_crop, "kernel_ms": crop_ms,
                          "kernel_share_of_step": crop_ms / (elapsed_ms / args.steps),

@@ -395,9 +395,16 @@ roi_align_fwd_sweep_kernel(const float* __restrict__ feat, RoiList L, int C, int
 //    from 784 taps to ~100-300; large RoIs degrade gracefully to the direct 784.
 constexpr int kTblBytes = 256;   // 14 x-entries + 2 y-entries of 16 B
 
-template <int XI>
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));   // not volatile: loads of an item may reorder
+  return v;
+}
+
+template <int XI, int S>
 __global__ void __launch_bounds__(kSweepThreads, 1)
-roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int PH, int S, int Rr,
+roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int PH, int /*S_rt*/, int Rr,
                             int St, int span_max, int nsteps, int items_stride, SweepWs ws,
                             float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
@@ -418,7 +425,7 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
   // dynamic shared: [table slots][ring][zero pixel][staging tiles]
   char* tbl = reinterpret_cast<char*>(smem) + (size_t)warp * 2 * kTblBytes;
   float* ring = smem + (size_t)kSweepWarps * 2 * kTblBytes / sizeof(float);
-  char* ring_b = reinterpret_cast<char*>(ring);
+  const uint32_t ring_s = smem_u32(ring);
   float* zero_px = ring + (size_t)Rr * row_words;
   float* stage = zero_px + kPad + (size_t)warp * kCh * PW;
   if (tid < kPad) zero_px[tid] = 0.0f;
@@ -502,38 +509,30 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
       if (ring_step) {
         mbar_wait(&bars[warp][slot], (parity >> slot) & 1u);
         parity ^= 1u << slot;
-        const float4* xt = reinterpret_cast<const float4*>(tbl + slot * kTblBytes);
-        const float4* yt = reinterpret_cast<const float4*>(tbl + slot * kTblBytes + 224);
-        // rows: (ylo0, yhi0[, ylo1, yhi1]) as byte pointers incl. the lane's channel, with weights
-        const char* rb[4];
-        float rw[4];
+        // shared-window byte addresses; every tap below is one LDS [reg + imm]
+        const float4* tb = reinterpret_cast<const float4*>(tbl + slot * kTblBytes);
+        uint32_t rb0, rb1, rb2, rb3;
+        float rw0, rw1, rw2, rw3;
         {
-          const float4 t0 = yt[0];
-          rb[0] = ring_b + (size_t)(__float_as_int(t0.x) + lane) * 4;
-          rb[1] = ring_b + (size_t)(__float_as_int(t0.y) + lane) * 4;
-          rw[0] = t0.z;
-          rw[1] = t0.w;
+          const float4 t0 = tb[14];
+          rb0 = ring_s + (uint32_t)(__float_as_int(t0.x) + lane) * 4u;
+          rb1 = ring_s + (uint32_t)(__float_as_int(t0.y) + lane) * 4u;
+          rw0 = t0.z;
+          rw1 = t0.w;
+          rb2 = rb3 = rb0;
+          rw2 = rw3 = 0.0f;
           if (S > 1) {
-            const float4 t1 = yt[1];
-            rb[2] = ring_b + (size_t)(__float_as_int(t1.x) + lane) * 4;
-            rb[3] = ring_b + (size_t)(__float_as_int(t1.y) + lane) * 4;
-            rw[2] = t1.z;
-            rw[3] = t1.w;
-          } else {
-            rb[2] = rb[3] = rb[0];
-            rw[2] = rw[3] = 0.0f;
+            const float4 t1 = tb[15];
+            rb2 = ring_s + (uint32_t)(__float_as_int(t1.x) + lane) * 4u;
+            rb3 = ring_s + (uint32_t)(__float_as_int(t1.y) + lane) * 4u;
+            rw2 = t1.z;
+            rw3 = t1.w;
           }
         }
-        auto G = [&](int col_bytes) {
-          float g = rw[0] * *reinterpret_cast<const float*>(rb[0] + col_bytes);
-          g = fmaf(rw[1], *reinterpret_cast<const float*>(rb[1] + col_bytes), g);
-          if (S > 1) {
-            g = fmaf(rw[2], *reinterpret_cast<const float*>(rb[2] + col_bytes), g);
-            g = fmaf(rw[3], *reinterpret_cast<const float*>(rb[3] + col_bytes), g);
-          }
-          return g;
-        };
-        int cur = -1000000;            // byte offset of the pixel whose G is in g_lo
+        // Column walk, branch free.  The pixel held in g_lo after sample k is always xl_k, so whether
+        // sample k can reuse / slide / must reload depends only on xl_k - xl_{k-1}: every predicate and
+        // every tap address comes straight from the table, and all loads of an item are independent.
+        uint32_t prev = 0x7fffffffu;
         float g_lo = 0.0f, g_hi = 0.0f;
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
@@ -541,17 +540,32 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
 #pragma unroll
           for (int ix = 0; ix < 2; ++ix) {
             if (ix < S) {
-              const float4 t = xt[pw * S + ix];
-              const int xl = __float_as_int(t.x) * 4;
-              const int d = xl - cur;
-              if (d == kPad * 4) {            // next pixel: slide
-                g_lo = g_hi;
-                g_hi = G(xl + kPad * 4);
-              } else if (d != 0) {            // anywhere else: evaluate both
-                g_lo = G(xl);
-                g_hi = G(xl + kPad * 4);
+              const float4 t = tb[pw * S + ix];
+              const uint32_t xl = (uint32_t)__float_as_int(t.x) * 4u;
+              const uint32_t d = xl - prev;
+              prev = xl;
+              const bool p_hi = d != 0u;
+              const bool p_lo = p_hi && d != (uint32_t)(kPad * 4);
+              const uint32_t a0 = rb0 + xl, a1 = rb1 + xl, a2 = rb2 + xl, a3 = rb3 + xl;
+              float nlo = 0.0f, nhi = 0.0f;
+              if (p_lo) {
+                nlo = rw0 * lds_f32<0>(a0);
+                nlo = fmaf(rw1, lds_f32<0>(a1), nlo);
+                if (S > 1) {
+                  nlo = fmaf(rw2, lds_f32<0>(a2), nlo);
+                  nlo = fmaf(rw3, lds_f32<0>(a3), nlo);
+                }
               }
-              cur = xl;
+              if (p_hi) {
+                nhi = rw0 * lds_f32<kPad * 4>(a0);
+                nhi = fmaf(rw1, lds_f32<kPad * 4>(a1), nhi);
+                if (S > 1) {
+                  nhi = fmaf(rw2, lds_f32<kPad * 4>(a2), nhi);
+                  nhi = fmaf(rw3, lds_f32<kPad * 4>(a3), nhi);
+                }
+              }
+              g_lo = p_lo ? nlo : (p_hi ? g_hi : g_lo);
+              g_hi = p_hi ? nhi : g_hi;
               acc = fmaf(t.z, g_lo, acc);
               acc = fmaf(t.w, g_hi, acc);
             }
@@ -626,10 +640,17 @@ static int launch_sweep(const SweepPlan& p, int F, int C, int H, int W, const fl
   dim3 grid(ceil_div(C, kCh), F, split);
   if (SMAX == 2 && PW == 7) {
     const size_t smem = p.ring_bytes + p.stage_bytes + (size_t)kSweepWarps * 2 * kTblBytes;
-    B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep7_kernel<XI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    roi_align_fwd_sweep7_kernel<XI><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, S, p.Rr, p.St, p.span_max,
-                                                                      p.nsteps, items_stride, ws, out);
+    if (S == 2) {
+      B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep7_kernel<XI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      roi_align_fwd_sweep7_kernel<XI, 2><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, S, p.Rr, p.St,
+                                                                           p.span_max, p.nsteps, items_stride, ws, out);
+    } else {
+      B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep7_kernel<XI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      roi_align_fwd_sweep7_kernel<XI, 1><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, S, p.Rr, p.St,
+                                                                           p.span_max, p.nsteps, items_stride, ws, out);
+    }
     B2D_LAUNCHED();
     return B2D_OK;
   }
