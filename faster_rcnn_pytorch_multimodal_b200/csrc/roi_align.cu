@@ -23,7 +23,7 @@
 
 namespace b2d {
 
-size_t sweep_workspace_bytes(int F, int H, int n_list);
+size_t sweep_workspace_bytes(int F, int H, int n_list, int per_frame);
 int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
                             float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
                             cudaStream_t st);
@@ -280,9 +280,10 @@ static int launch_fwd_planes(int F, int C, int H, int W, const float* feat, cons
 
 using namespace b2d;
 
-extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W*/, int num_rois) {
+extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W*/, int num_rois, int per_frame) {
   if (F <= 0 || H <= 0 || num_rois <= 0) return 0;
-  return sweep_workspace_bytes(F, H, num_rois);
+  if (per_frame <= 0 || per_frame > num_rois) per_frame = num_rois;
+  return sweep_workspace_bytes(F, H, num_rois, per_frame);
 }
 
 extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,

@@ -48,7 +48,7 @@ static SweepPlan plan_sweep(int H, int W, int PW) {
   const size_t row_bytes = (size_t)W * kPad * sizeof(float);
   const int pwp = PW | 1;
   p.stage_bytes = (size_t)kSweepWarps * kCh * pwp * sizeof(float) + kPad * sizeof(float);
-  const size_t budget = 227 * 1024 - 1024 - p.stage_bytes - (size_t)kSweepWarps * 2 * 256;   // 1 KB static shared, table slots
+  const size_t budget = 227 * 1024 - 1024 - p.stage_bytes - (size_t)kSweepWarps * 272;   // 1 KB static shared, record slots
   int Rr = (int)(budget / row_bytes);
   const int xi_t = p.XI <= 4 ? p.XI : (p.XI <= 6 ? 6 : 12);
   if (p.XI > 12 || Rr < 5) { p.ok = false; return p; }
@@ -71,7 +71,8 @@ struct SweepWs {
   float4* ytab;        // [n_list][PH*S]  {slot(ylo)*W*33, slot(yhi)*W*33 (int bits), w_lo, w_hi}
   float* count;        // [n_list] samples per bin
   int32_t* bucket_of;  // [n_list][PH]
-  uint32_t* items;     // [F][items_stride]  (entry << 4) | ph, grouped by bucket
+  uint32_t* items;     // [F][items_stride]  (entry << 4) | ph, grouped by bucket (generic kernel)
+  float4* records;     // [F][items_stride][17] self-contained item records (fast path)
   int32_t* bucket_start;  // [F][nb + 1]
   float scale;            // spatial_scale / aligned, for the in-kernel slow path
   int aligned;
@@ -92,7 +93,8 @@ static SweepWs carve_sweep(void* base, int F, int n_list, int per_frame, int H) 
   w.count = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n_list));
   w.bucket_of = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)n_list * kMaxPool));
   w.items = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)F * per_frame * kMaxPool));
-  w.bucket_start = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * (H + 3)));
+  w.records = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)F * per_frame * 8 * 17));   // fast path: PH <= 8
+  w.bucket_start = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * (H + 4)));
   w.bytes = off;
   return w;
 }
@@ -384,16 +386,23 @@ roi_align_fwd_sweep_kernel(const float* __restrict__ feat, RoiList L, int C, int
 
 // ------------------------------------------------------------------------------------------
 // Fast path: PW == 7, sampling_ratio 1 or 2 (cfg.POOLING_SIZE = 7, model/config.py:367).
-//  * per-warp tap tables live in shared memory, double buffered and filled by 1-D bulk TMA
-//    (cp.async.bulk + mbarrier) one item ahead, across step boundaries: no table load ever
-//    sits on the critical path;
-//  * separable evaluation with column reuse: for a pixel column x the row-combined value
-//        G(x) = sum_iy  hy[iy]*F[ylo[iy]][x] + ly[iy]*F[yhi[iy]][x]
-//    is shared by every sample column that touches x.  Sample columns are walked left to right
-//    keeping G(cur) and G(cur+1); when the next sample's x_low is the same pixel or the next one
-//    (always, for RoIs up to ~14 feature pixels wide) only one new G is evaluated.  Small RoIs drop
-//    from 784 taps to ~100-300; large RoIs degrade gracefully to the direct 784.
-constexpr int kTblBytes = 256;   // 14 x-entries + 2 y-entries of 16 B
+//
+// The prep kernel emits one self-contained 272-byte RECORD per work item (roi, bin-row), already
+// in bucket order, so the main kernel does no per-item bookkeeping at all: a warp prefetches its
+// next record into registers (17 lanes x 16 B, coalesced) while it computes the current one, drops
+// it into a per-warp shared slot and runs class-specialised STRAIGHT-LINE code on it:
+//   record[0]     = {roi row r, ph, class, x0 byte offset}
+//   record[1]     = ring word offsets of the four pixel rows {ylo0, yhi0, ylo1, yhi1}
+//   record[2]     = their weights, pre-divided by the sample count
+//   record[3..16] = class 0 "dense8": Wx[7][8]; the bin-row touches <= 8 consecutive pixel columns
+//                   x0..x0+7; evaluate G(x0+j) = sum_rows w*F[row][x0+j] once per column (32 taps,
+//                   immediate offsets) and contract with the dense 7x8 weights: 152 instructions
+//                   and 56 shared wavefronts instead of 784 taps;
+//                   class 1 "direct": 14 sample columns {xl byte offset, -, hx, lx}: G at xl and
+//                   xl+1 for every sample (the stock 16 taps per bin), no reuse;
+//                   class 2: bin-row taller than the ring, evaluated from global memory (rare).
+constexpr int kRecVec = 17;                 // float4 per record
+constexpr int kRecBytes = kRecVec * 16;     // 272
 
 template <int OFF>
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -402,13 +411,156 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+// prep for the fast path: one thread per (entry, ph) item
+template <int S>
+__global__ void __launch_bounds__(512)
+roi_sweep7_prep_kernel(RoiList L, int H, int W, int PH, float scale, int aligned, int Rr, int St, int span_max,
+                       int nsteps, int items_stride, SweepWs ws) {
+  extern __shared__ int s_buckets[];   // [nb] counts, [nb] offsets, [nb] fill
+  constexpr int PW = 7;
+  const int nb = nsteps + 1;
+  int* cnt = s_buckets;
+  int* offs = s_buckets + nb;
+  int* fill = s_buckets + 2 * nb;
+  const int f = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) s_buckets[i] = 0;
+  __syncthreads();
+  int first = 0, n_ent = L.n;
+  if (L.seg_count) {
+    first = f * L.seg_stride;
+    n_ent = L.seg_count[f];
+  }
+  const int n_items = n_ent * PH;
+  // pass A: bucket of every item
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+    const int e = first + i / PH, ph = i - (i / PH) * PH;
+    const int r = L.ids ? L.ids[e] : e;
+    const float* roi = L.rois + (size_t)r * 5;
+    int bucket = -1;
+    if (L.seg_count || (int)roi[0] == f) {
+      const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
+      const RoiGeom g = roi_geometry(rr, scale, PH, PW, S, aligned != 0);
+      int y_first = H, y_last = -1;
+      for (int iy = 0; iy < S; ++iy) {
+        const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
+        if (t.ok) {
+          y_first = min(y_first, t.lo);
+          y_last = max(y_last, t.hi);
+        }
+      }
+      if (y_last < 0) bucket = 0;
+      else if (y_last - y_first + 1 > span_max) bucket = nsteps;
+      else bucket = y_first / St;
+      atomicAdd(&cnt[bucket], 1);
+    }
+    ws.bucket_of[(size_t)e * PH + ph] = bucket;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    int32_t* bs = ws.bucket_start + (size_t)f * (nb + 2);
+    for (int b = 0; b < nb; ++b) {
+      offs[b] = run;
+      bs[b] = run;
+      run += cnt[b];
+    }
+    bs[nb] = run;
+    bs[nb + 1] = run;
+  }
+  __syncthreads();
+  // pass B: records
+  float4* recs = ws.records + (size_t)f * items_stride * kRecVec;
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+    const int e = first + i / PH, ph = i - (i / PH) * PH;
+    const int bucket = ws.bucket_of[(size_t)e * PH + ph];
+    if (bucket < 0) continue;
+    const int r = L.ids ? L.ids[e] : e;
+    const float* roi = L.rois + (size_t)r * 5;
+    const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
+    const RoiGeom g = roi_geometry(rr, scale, PH, PW, S, aligned != 0);
+    float4* rec = recs + (size_t)(offs[bucket] + atomicAdd(&fill[bucket], 1)) * kRecVec;
+    // rows
+    int y_first = 0;
+    {
+      int yf = H;
+      for (int iy = 0; iy < S; ++iy) {
+        const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
+        if (t.ok) yf = min(yf, t.lo);
+      }
+      if (yf < H) y_first = yf;
+    }
+    int yo[4];
+    float yw[4];
+    const float inv_cnt = 1.0f / g.count;
+    for (int iy = 0; iy < 2; ++iy) {
+      AxisTap t;
+      t.lo = t.hi = y_first;
+      t.wlo = t.whi = 0.0f;
+      t.ok = false;
+      if (iy < S) {
+        t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
+        if (!t.ok) t.lo = t.hi = y_first;
+      }
+      yo[2 * iy] = (t.lo % Rr) * W * kPad;
+      yo[2 * iy + 1] = (t.hi % Rr) * W * kPad;
+      yw[2 * iy] = t.wlo * inv_cnt;
+      yw[2 * iy + 1] = t.whi * inv_cnt;
+    }
+    rec[1] = make_float4(__int_as_float(yo[0]), __int_as_float(yo[1]), __int_as_float(yo[2]), __int_as_float(yo[3]));
+    rec[2] = make_float4(yw[0], yw[1], yw[2], yw[3]);
+    // columns
+    int x0 = W, x1 = -1;
+    for (int k = 0; k < PW * S; ++k) {
+      const AxisTap t = axis_tap(g.start_w, g.bin_w, k / S, k % S, S, W);
+      if (t.ok) {
+        x0 = min(x0, t.lo);
+        x1 = max(x1, t.hi);
+      }
+    }
+    int cls;
+    if (bucket == nsteps) {
+      cls = 2;
+      x0 = 0;
+    } else if (x1 < 0) {                      // no valid sample column: all-zero dense weights
+      cls = 0;
+      x0 = 0;
+      for (int v = 3; v < kRecVec; ++v) rec[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (x1 - x0 + 1 <= 8) {
+      cls = 0;
+      for (int pw = 0; pw < PW; ++pw) {
+        float wx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ix = 0; ix < S; ++ix) {
+          const AxisTap t = axis_tap(g.start_w, g.bin_w, pw, ix, S, W);
+          if (!t.ok) continue;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (t.lo - x0 == j) wx[j] += t.wlo;
+            if (t.hi - x0 == j) wx[j] += t.whi;
+          }
+        }
+        rec[3 + 2 * pw] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+        rec[4 + 2 * pw] = make_float4(wx[4], wx[5], wx[6], wx[7]);
+      }
+    } else {
+      cls = 1;
+      for (int k = 0; k < 14; ++k) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < PW * S) {
+          const AxisTap t = axis_tap(g.start_w, g.bin_w, k / S, k % S, S, W);
+          v = make_float4(__int_as_float(t.lo * kPad * 4), 0.f, t.wlo, t.whi);   // hi tap = lo + 1 pixel (weight 0 at the border)
+        }
+        rec[3 + k] = v;
+      }
+    }
+    rec[0] = make_float4(__int_as_float(r), __int_as_float(ph), __int_as_float(cls), __int_as_float(x0 * kPad * 4));
+  }
+}
+
 template <int XI, int S>
 __global__ void __launch_bounds__(kSweepThreads, 1)
-roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int PH, int /*S_rt*/, int Rr,
-                            int St, int span_max, int nsteps, int items_stride, SweepWs ws,
-                            float* __restrict__ out) {
+roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int PH, int Rr, int St,
+                            int span_max, int nsteps, int items_stride, SweepWs ws, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t bars[kSweepWarps][2];
   constexpr int PW = 7;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y;
@@ -416,27 +568,31 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
   const int nch = min(kCh, C - c0);
   const int split = gridDim.z, part = blockIdx.z;
   const int stride = kSweepWarps * split;
+  const int my_off = part * kSweepWarps + warp;
   const int bins = PH * PW;
   const int nb = nsteps + 1;
   const int row_words = W * kPad;
-  const int32_t* bstart = ws.bucket_start + (size_t)f * (nb + 1);
-  const uint32_t* items = ws.items + (size_t)f * items_stride;
+  const int32_t* bstart = ws.bucket_start + (size_t)f * (nb + 2);
+  const float4* recs = ws.records + (size_t)f * items_stride * kRecVec;
   const float* fbase = feat + ((size_t)f * C + c0) * H * W;
-  // dynamic shared: [table slots][ring][zero pixel][staging tiles]
-  char* tbl = reinterpret_cast<char*>(smem) + (size_t)warp * 2 * kTblBytes;
-  float* ring = smem + (size_t)kSweepWarps * 2 * kTblBytes / sizeof(float);
+  // dynamic shared: [record slots][ring][zero pixel][staging tiles]
+  float4* slot = reinterpret_cast<float4*>(smem) + (size_t)warp * kRecVec;
+  float* ring = smem + (size_t)kSweepWarps * kRecBytes / sizeof(float);
   const uint32_t ring_s = smem_u32(ring);
   float* zero_px = ring + (size_t)Rr * row_words;
   float* stage = zero_px + kPad + (size_t)warp * kCh * PW;
   if (tid < kPad) zero_px[tid] = 0.0f;
-  if (lane == 0) {
-    mbar_init(&bars[warp][0], 1);
-    mbar_init(&bars[warp][1], 1);
-  }
-  unsigned cpack0 = 0u, cpack1 = 0u;   // channel of flat index lane + 32*j, 5 bits each (j = 0..6)
+
+  // output scatter pattern of this lane: flat index lane + 32*j of the [32][7] tile -> channel c_j
+  int ooff[PW];
+  unsigned omask = 0u;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) cpack0 |= (unsigned)((lane + 32 * j) / PW) << (5 * j);
-  cpack1 = (unsigned)((lane + 32 * 6) / PW);
+  for (int j = 0; j < PW; ++j) {
+    const int idx = lane + 32 * j;
+    const int c = idx / PW;
+    ooff[j] = idx + c * (bins - PW);
+    if (c < nch) omask |= 1u << j;
+  }
 
   const int resident0 = min(H, St + span_max - 1);
   for (int pr = warp; pr < kCh * resident0; pr += kSweepWarps) {
@@ -447,39 +603,13 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
       for (int x = lane; x < W; x += 32) dst[x * kPad] = __ldg(src + x);
     }
   }
-
-  // ---- this warp's item sequence (crosses buckets): position = (bucket k, index it)
-  auto first_in = [&](int k) { return bstart[k] + part * kSweepWarps + warp; };
-  auto normalize = [&](int& k, int& it) {
-    while (k < nb && it >= bstart[k + 1]) {
-      ++k;
-      if (k < nb) it = first_in(k);
-    }
-  };
-  const uint32_t xbytes = (uint32_t)(PW * S * 16), ybytes = (uint32_t)(S * 16);
-  auto issue_tables = [&](int slot, uint32_t code) {   // one lane
-    const int e = (int)(code >> 4), ph = (int)(code & 15u);
-    char* dst = tbl + slot * kTblBytes;
-    mbar_expect_tx(&bars[warp][slot], xbytes + ybytes);
-    bulk_g2s(dst, ws.xtab + (size_t)e * PW * S, xbytes, &bars[warp][slot]);
-    bulk_g2s(dst + 224, ws.ytab + ((size_t)e * PH + ph) * S, ybytes, &bars[warp][slot]);
-  };
-
-  int kc = 0, itc = first_in(0);
-  normalize(kc, itc);
-  int kn = kc, itn = itc + stride;
-  normalize(kn, itn);
-  uint32_t codec = kc < nb ? __ldg(items + itc) : 0u;
-  uint32_t coden = kn < nb ? __ldg(items + itn) : 0u;
-  __syncthreads();                     // ring prologue + mbarrier init visible
-  unsigned parity = 0u;                // bit s = phase of slot s
-  int slot = 0;
-  if (lane == 0 && kc < nsteps) issue_tables(0, codec);
+  __syncthreads();
 
   constexpr int kPairs = kMaxPF / XI;
   float pf[kMaxPF];
   int p0 = resident0, slot0 = resident0 % Rr;
-  const float inv_cnt = 1.0f / (float)(S * S);
+  float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  int have = -1;                          // item index whose record sits in rec_next
 
   for (int k = 0; k <= nsteps; ++k) {
     const bool ring_step = k < nsteps;
@@ -498,97 +628,91 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
         }
       }
     }
-    while (kc == k) {
-      // look two items ahead for the code, one ahead for the tables
-      int k2 = kn, it2 = itn + stride;
-      normalize(k2, it2);
-      const uint32_t code2 = k2 < nb ? __ldg(items + it2) : 0u;
-      if (lane == 0 && kn < nsteps) issue_tables(slot ^ 1, coden);
-      const int e = (int)(codec >> 4), ph = (int)(codec & 15u);
-      const int r = L.ids ? L.ids[e] : e;
-      if (ring_step) {
-        mbar_wait(&bars[warp][slot], (parity >> slot) & 1u);
-        parity ^= 1u << slot;
-        // shared-window byte addresses; every tap below is one LDS [reg + imm]
-        const float4* tb = reinterpret_cast<const float4*>(tbl + slot * kTblBytes);
-        uint32_t rb0, rb1, rb2, rb3;
-        float rw0, rw1, rw2, rw3;
-        {
-          const float4 t0 = tb[14];
-          rb0 = ring_s + (uint32_t)(__float_as_int(t0.x) + lane) * 4u;
-          rb1 = ring_s + (uint32_t)(__float_as_int(t0.y) + lane) * 4u;
-          rw0 = t0.z;
-          rw1 = t0.w;
-          rb2 = rb3 = rb0;
-          rw2 = rw3 = 0.0f;
-          if (S > 1) {
-            const float4 t1 = tb[15];
-            rb2 = ring_s + (uint32_t)(__float_as_int(t1.x) + lane) * 4u;
-            rb3 = ring_s + (uint32_t)(__float_as_int(t1.y) + lane) * 4u;
-            rw2 = t1.z;
-            rw3 = t1.w;
-          }
-        }
-        // Column walk, branch free.  The pixel held in g_lo after sample k is always xl_k, so whether
-        // sample k can reuse / slide / must reload depends only on xl_k - xl_{k-1}: every predicate and
-        // every tap address comes straight from the table, and all loads of an item are independent.
-        uint32_t prev = 0x7fffffffu;
-        float g_lo = 0.0f, g_hi = 0.0f;
+    const int i1 = bstart[k + 1], i2 = bstart[k + 2];
+    for (int it = bstart[k] + my_off; it < i1; it += stride) {
+      if (have != it && lane < kRecVec) rec_next = __ldg(recs + (size_t)it * kRecVec + lane);
+      __syncwarp();
+      if (lane < kRecVec) slot[lane] = rec_next;
+      __syncwarp();
+      int nxt = it + stride;
+      if (nxt >= i1) {
+        nxt = i1 + my_off;               // my first item of the next bucket, if any
+        if (nxt >= i2) nxt = -1;
+      }
+      have = nxt;
+      if (nxt >= 0 && lane < kRecVec) rec_next = __ldg(recs + (size_t)nxt * kRecVec + lane);
+
+      const float4 hdr = slot[0];
+      const int r = __float_as_int(hdr.x), ph = __float_as_int(hdr.y), cls = __float_as_int(hdr.z);
+      if (cls != 2) {
+        const float4 ro = slot[1], rw = slot[2];
+        const uint32_t xb = (uint32_t)__float_as_int(hdr.w) + (uint32_t)lane * 4u + ring_s;
+        const uint32_t a0 = xb + (uint32_t)__float_as_int(ro.x) * 4u, a1 = xb + (uint32_t)__float_as_int(ro.y) * 4u;
+        const uint32_t a2 = xb + (uint32_t)__float_as_int(ro.z) * 4u, a3 = xb + (uint32_t)__float_as_int(ro.w) * 4u;
+        if (cls == 0) {
+          float G[8];
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw) {
-          float acc = 0.0f;
-#pragma unroll
-          for (int ix = 0; ix < 2; ++ix) {
-            if (ix < S) {
-              const float4 t = tb[pw * S + ix];
-              const uint32_t xl = (uint32_t)__float_as_int(t.x) * 4u;
-              const uint32_t d = xl - prev;
-              prev = xl;
-              const bool p_hi = d != 0u;
-              const bool p_lo = p_hi && d != (uint32_t)(kPad * 4);
-              const uint32_t a0 = rb0 + xl, a1 = rb1 + xl, a2 = rb2 + xl, a3 = rb3 + xl;
-              float nlo = 0.0f, nhi = 0.0f;
-              if (p_lo) {
-                nlo = rw0 * lds_f32<0>(a0);
-                nlo = fmaf(rw1, lds_f32<0>(a1), nlo);
-                if (S > 1) {
-                  nlo = fmaf(rw2, lds_f32<0>(a2), nlo);
-                  nlo = fmaf(rw3, lds_f32<0>(a3), nlo);
-                }
-              }
-              if (p_hi) {
-                nhi = rw0 * lds_f32<kPad * 4>(a0);
-                nhi = fmaf(rw1, lds_f32<kPad * 4>(a1), nhi);
-                if (S > 1) {
-                  nhi = fmaf(rw2, lds_f32<kPad * 4>(a2), nhi);
-                  nhi = fmaf(rw3, lds_f32<kPad * 4>(a3), nhi);
-                }
-              }
-              g_lo = p_lo ? nlo : (p_hi ? g_hi : g_lo);
-              g_hi = p_hi ? nhi : g_hi;
-              acc = fmaf(t.z, g_lo, acc);
-              acc = fmaf(t.w, g_hi, acc);
+          for (int j = 0; j < 8; ++j) {
+            float g;
+            switch (j) {   // immediate offsets j * 132
+              case 0: g = rw.x * lds_f32<0>(a0); g = fmaf(rw.y, lds_f32<0>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<0>(a2), g); g = fmaf(rw.w, lds_f32<0>(a3), g); } break;
+              case 1: g = rw.x * lds_f32<132>(a0); g = fmaf(rw.y, lds_f32<132>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<132>(a2), g); g = fmaf(rw.w, lds_f32<132>(a3), g); } break;
+              case 2: g = rw.x * lds_f32<264>(a0); g = fmaf(rw.y, lds_f32<264>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<264>(a2), g); g = fmaf(rw.w, lds_f32<264>(a3), g); } break;
+              case 3: g = rw.x * lds_f32<396>(a0); g = fmaf(rw.y, lds_f32<396>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<396>(a2), g); g = fmaf(rw.w, lds_f32<396>(a3), g); } break;
+              case 4: g = rw.x * lds_f32<528>(a0); g = fmaf(rw.y, lds_f32<528>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<528>(a2), g); g = fmaf(rw.w, lds_f32<528>(a3), g); } break;
+              case 5: g = rw.x * lds_f32<660>(a0); g = fmaf(rw.y, lds_f32<660>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<660>(a2), g); g = fmaf(rw.w, lds_f32<660>(a3), g); } break;
+              case 6: g = rw.x * lds_f32<792>(a0); g = fmaf(rw.y, lds_f32<792>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<792>(a2), g); g = fmaf(rw.w, lds_f32<792>(a3), g); } break;
+              default: g = rw.x * lds_f32<924>(a0); g = fmaf(rw.y, lds_f32<924>(a1), g); if (S > 1) { g = fmaf(rw.z, lds_f32<924>(a2), g); g = fmaf(rw.w, lds_f32<924>(a3), g); } break;
             }
+            G[j] = g;
           }
-          stage[lane * PW + pw] = acc * inv_cnt;
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw) {
+            const float4 wa = slot[3 + 2 * pw], wb = slot[4 + 2 * pw];
+            float acc = wa.x * G[0];
+            acc = fmaf(wa.y, G[1], acc);
+            acc = fmaf(wa.z, G[2], acc);
+            acc = fmaf(wa.w, G[3], acc);
+            acc = fmaf(wb.x, G[4], acc);
+            acc = fmaf(wb.y, G[5], acc);
+            acc = fmaf(wb.z, G[6], acc);
+            acc = fmaf(wb.w, G[7], acc);
+            stage[lane * PW + pw] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int ix = 0; ix < S; ++ix) {
+              const float4 t = slot[3 + pw * S + ix];
+              // t.x is an absolute column byte offset; the record's x0 is already inside a0..a3
+              const uint32_t xo = (uint32_t)__float_as_int(t.x) - (uint32_t)__float_as_int(hdr.w);
+              float glo = rw.x * lds_f32<0>(a0 + xo), ghi = rw.x * lds_f32<132>(a0 + xo);
+              glo = fmaf(rw.y, lds_f32<0>(a1 + xo), glo);
+              ghi = fmaf(rw.y, lds_f32<132>(a1 + xo), ghi);
+              if (S > 1) {
+                glo = fmaf(rw.z, lds_f32<0>(a2 + xo), glo);
+                ghi = fmaf(rw.z, lds_f32<132>(a2 + xo), ghi);
+                glo = fmaf(rw.w, lds_f32<0>(a3 + xo), glo);
+                ghi = fmaf(rw.w, lds_f32<132>(a3 + xo), ghi);
+              }
+              acc = fmaf(t.z, glo, acc);
+              acc = fmaf(t.w, ghi, acc);
+            }
+            stage[lane * PW + pw] = acc;
+          }
         }
         __syncwarp();
         float* o = out + ((size_t)r * C + c0) * bins + ph * PW;
-        const int skip_o = bins - PW;
 #pragma unroll
-        for (int j = 0; j < PW; ++j) {
-          const int idx = lane + 32 * j;
-          const int c = j < 6 ? (int)((cpack0 >> (5 * j)) & 31u) : (int)cpack1;
-          if (c < nch) o[idx + c * skip_o] = stage[idx];
-        }
-        __syncwarp();
-        slot ^= 1;
+        for (int j = 0; j < PW; ++j)
+          if (omask & (1u << j)) o[ooff[j]] = stage[lane + 32 * j];
       } else {
-        // slow path (bucket nsteps): bin-row spans more rows than the ring; taps straight from global
+        // class 2: bin-row spans more rows than the ring; taps straight from global memory
         const bool ch_ok = lane < nch;
         const float* roi = L.rois + (size_t)r * 5;
         const float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
-        // scale / aligned are folded into the tables for the ring path; recover them from the prep's inputs
         const RoiGeom g = roi_geometry(rr, ws.scale, PH, PW, S, ws.aligned != 0);
         const float* plane = fbase + (size_t)(ch_ok ? lane : 0) * H * W;
         for (int pw = 0; pw < PW; ++pw) {
@@ -606,8 +730,6 @@ roi_align_fwd_sweep7_kernel(const float* __restrict__ feat, RoiList L, int C, in
           if (ch_ok) out[((size_t)r * C + c0 + lane) * bins + ph * PW + pw] = acc / g.count;
         }
       }
-      kc = kn; itc = itn; codec = coden;
-      kn = k2; itn = it2; coden = code2;
     }
     if (prow > 0) {
 #pragma unroll
@@ -638,22 +760,33 @@ static int launch_sweep(const SweepPlan& p, int F, int C, int H, int W, const fl
                         int PW, float scale, int S, int aligned, int items_stride, const SweepWs& ws, int split,
                         float* out, cudaStream_t st) {
   dim3 grid(ceil_div(C, kCh), F, split);
-  if (SMAX == 2 && PW == 7) {
-    const size_t smem = p.ring_bytes + p.stage_bytes + (size_t)kSweepWarps * 2 * kTblBytes;
+  const int nb = p.nsteps + 1;
+  if (SMAX == 2 && PW == 7 && PH <= 8) {
+    const size_t smem = p.ring_bytes + p.stage_bytes + (size_t)kSweepWarps * kRecBytes;
+    const int rec_stride = items_stride / kMaxPool * 8;     // records region holds 8 bin-rows per entry
     if (S == 2) {
+      roi_sweep7_prep_kernel<2><<<F, 512, sizeof(int) * 3 * nb, st>>>(L, H, W, PH, scale, aligned, p.Rr, p.St, p.span_max,
+                                                                     p.nsteps, rec_stride, ws);
+      B2D_LAUNCHED();
       B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep7_kernel<XI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      roi_align_fwd_sweep7_kernel<XI, 2><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, S, p.Rr, p.St,
-                                                                           p.span_max, p.nsteps, items_stride, ws, out);
+      roi_align_fwd_sweep7_kernel<XI, 2><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, p.Rr, p.St, p.span_max,
+                                                                           p.nsteps, rec_stride, ws, out);
     } else {
+      roi_sweep7_prep_kernel<1><<<F, 512, sizeof(int) * 3 * nb, st>>>(L, H, W, PH, scale, aligned, p.Rr, p.St, p.span_max,
+                                                                     p.nsteps, rec_stride, ws);
+      B2D_LAUNCHED();
       B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep7_kernel<XI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      roi_align_fwd_sweep7_kernel<XI, 1><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, S, p.Rr, p.St,
-                                                                           p.span_max, p.nsteps, items_stride, ws, out);
+      roi_align_fwd_sweep7_kernel<XI, 1><<<grid, kSweepThreads, smem, st>>>(feat, L, C, H, W, PH, p.Rr, p.St, p.span_max,
+                                                                           p.nsteps, rec_stride, ws, out);
     }
     B2D_LAUNCHED();
     return B2D_OK;
   }
+  roi_sweep_prep_kernel<<<F, 256, sizeof(int) * 3 * nb, st>>>(L, H, W, PH, PW, scale, S, aligned, p.Rr, p.St, p.span_max,
+                                                             p.nsteps, items_stride, ws);
+  B2D_LAUNCHED();
   const size_t smem = p.ring_bytes + p.stage_bytes;
   B2D_CUDA(cudaFuncSetAttribute(roi_align_fwd_sweep_kernel<SMAX, XI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
@@ -663,7 +796,9 @@ static int launch_sweep(const SweepPlan& p, int F, int C, int H, int W, const fl
   return B2D_OK;
 }
 
-size_t sweep_workspace_bytes(int F, int H, int n_list) { return carve_sweep(nullptr, F, n_list, n_list, H).bytes; }
+size_t sweep_workspace_bytes(int F, int H, int n_list, int per_frame) {
+  return carve_sweep(nullptr, F, n_list, per_frame, H).bytes;
+}
 
 // Returns B2D_ERR_UNSUPPORTED when this path does not apply (caller falls back).
 int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
@@ -678,10 +813,6 @@ int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const
   ws.scale = scale;
   ws.aligned = aligned;
   const int items_stride = per_frame * kMaxPool;
-  const int nb = p.nsteps + 1;
-  roi_sweep_prep_kernel<<<F, 256, sizeof(int) * 3 * nb, st>>>(L, H, W, PH, PW, scale, S, aligned, p.Rr, p.St, p.span_max,
-                                                             p.nsteps, items_stride, ws);
-  B2D_LAUNCHED();
   if (L.seg_count) {
     dim3 zg(L.seg_stride, F);
     roi_zero_pad_kernel<<<zg, 256, 0, st>>>(L, C * PH * PW, out);

@@ -153,7 +153,9 @@ def _roi_align_forward(feat, rois, out_hw, scale, sampling_ratio, aligned, roi_i
         return out
     n_ids = 0 if roi_ids is None else roi_ids.numel()
     L = lib()
-    ws = workspaces.get(feat.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, max(R, n_ids)))
+    n_list = n_ids if roi_ids is not None else R
+    per_frame = int(seg_stride) if seg_count is not None else n_list
+    ws = workspaces.get(feat.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, n_list, per_frame))
     check(L.b2d_roi_align_forward(Fr, Cc, H, W, ptr(feat), ptr(rois), R, ptr(roi_ids), n_ids, ptr(seg_count),
                                   int(seg_stride), out_hw[0], out_hw[1], float(scale), int(sampling_ratio),
                                   int(bool(aligned)), ptr(out), ptr(ws), ws.numel(), stream_ptr(feat.device)),

@@ -124,7 +124,9 @@ int b2d_argsort_desc(int num_frames, int n, const float* scores, int32_t* order,
  *   unless accumulate != 0).
  * Backward is deterministic and uses no atomics.
  * ---------------------------------------------------------------------------------- */
-size_t b2d_roi_align_workspace_bytes(int num_frames, int channels, int height, int width, int num_rois);
+/* per_frame: most list entries one frame can own (seg_stride; or num_rois when frames filter by col0). */
+size_t b2d_roi_align_workspace_bytes(int num_frames, int channels, int height, int width, int num_rois,
+                                     int per_frame);
 int b2d_roi_align_forward(int num_frames, int channels, int height, int width,
                           const float* feat, const float* rois, int num_rois,
                           const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
