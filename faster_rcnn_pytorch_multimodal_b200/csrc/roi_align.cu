@@ -24,6 +24,10 @@
 namespace b2d {
 
 size_t sweep_workspace_bytes(int F, int H, int n_list, int per_frame);
+size_t rows_workspace_bytes(int F, int H, int per_frame);
+int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
+                           float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st);
 int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
                             float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
                             cudaStream_t st);
@@ -283,7 +287,8 @@ using namespace b2d;
 extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W*/, int num_rois, int per_frame) {
   if (F <= 0 || H <= 0 || num_rois <= 0) return 0;
   if (per_frame <= 0 || per_frame > num_rois) per_frame = num_rois;
-  return sweep_workspace_bytes(F, H, num_rois, per_frame);
+  const size_t a = sweep_workspace_bytes(F, H, num_rois, per_frame), b = rows_workspace_bytes(F, H, per_frame);
+  return a > b ? a : b;
 }
 
 extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
@@ -297,6 +302,12 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
   if (!rois) return B2D_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   // production path: channel-on-lanes sweep kernel (roi_align_sweep.cu); needs the workspace
+  // production path: 7x7 "rows" kernel (roi_align_rows.cu), then the generic sweep kernel; both need the workspace
+  if (C >= 16) {
+    const int rc = roi_align_forward_rows(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
+                                          workspace, workspace_bytes, st);
+    if (rc != B2D_ERR_UNSUPPORTED) return rc;
+  }
   if (C >= 16) {
     const int rc = roi_align_forward_sweep(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
                                            workspace, workspace_bytes, st);
