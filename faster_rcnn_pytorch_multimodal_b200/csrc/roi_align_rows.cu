@@ -35,46 +35,49 @@ namespace rows {
 constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
-constexpr int kMaxPF = 24;         // prefetch registers per thread
 constexpr int kP = 7;              // PH = PW = 7
 constexpr int kRecVec = 32;        // float4 per item record
 constexpr int kRecBytes = kRecVec * 16;
 constexpr int kMaxRows = 12;       // distinct feature rows per item
 constexpr int kXVec = 7;           // float4 of column taps {xo_a, lx_a, xo_b, lx_b}
 constexpr int kRowVec0 = 1 + kXVec;
+constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 
-constexpr int kXI = 4;                       // a loader "pair" is (channel, row, 128-column chunk)
-constexpr int kPairs = kMaxPF / kXI;         // pairs one warp prefetches per step
-
+// Ring geometry.  The ring holds nblk blocks of St rows.  Bucket k (items whose first row lies in
+// block k) may touch blocks k .. k + nbk - 1; the other nblk - nbk blocks are slack: they are being
+// refilled while slower warps still work on older buckets, so warps drift apart by up to that many
+// blocks instead of meeting at a barrier every step.
 struct Plan {
   int pitch;      // words per (slot, channel) row, = 1 mod 32 and > W
   int row_bytes;  // bytes per ring slot
-  int Rr, St, span_max, nsteps, nchunk, resident0;
+  int Rr, St, nblk, nbk, span_max, nsteps;
   size_t smem;
   bool ok;
 };
 
 static Plan make_plan(int H, int W) {
   Plan p{};
-  p.nchunk = ceil_div(W, 32 * kXI);
   p.pitch = ((W + 1 + 30) / 32) * 32 + 1;            // smallest value = 1 (mod 32) that is >= W + 1
   p.row_bytes = kCh * p.pitch * 4;
   const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * kCh * kP * 4 + 64;
-  const size_t budget = 227 * 1024 - 1024 - fixed;
+  const size_t budget = 227 * 1024 - 2048 - fixed;
   int Rr = (int)(budget / p.row_bytes);
   if (Rr < 6) { p.ok = false; return p; }
   if (Rr >= H) {
-    p.Rr = H; p.St = H; p.span_max = H; p.nsteps = 1; p.resident0 = H;
+    p.Rr = H; p.St = H; p.nblk = 1; p.nbk = 1; p.span_max = H; p.nsteps = 1;
   } else {
-    int St = kPairs * kWarps / (kCh * p.nchunk);     // rows one step can prefetch
-    if (St > Rr / 4) St = Rr / 4;
-    if (St < 1) { p.ok = false; return p; }
+    int St = Rr / 12;
+    if (St < 1) St = 1;
     Rr -= Rr % St;                                   // blocks of St rows never wrap inside the ring
-    p.Rr = Rr; p.St = St; p.span_max = Rr - 2 * St + 1; p.nsteps = ceil_div(H, St); p.resident0 = Rr - St;
+    const int nblk = Rr / St;
+    const int slack = nblk >= 12 ? 3 : (nblk >= 8 ? 2 : 1);
+    p.Rr = Rr; p.St = St; p.nblk = nblk; p.nbk = nblk - slack;
+    p.span_max = (p.nbk - 1) * St + 1;
+    p.nsteps = ceil_div(H, St);
   }
   if (p.span_max > kMaxRows) p.span_max = kMaxRows;
   p.smem = fixed + (size_t)p.Rr * p.row_bytes;
-  p.ok = p.span_max >= 4;
+  p.ok = p.span_max >= 4 && p.nblk <= kMaxBlk;
   return p;
 }
 
@@ -243,7 +246,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
         }
       }
       const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
-      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), 0.f, 0.f);
+      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(b), 0.f);
     });
   }
 }
@@ -265,7 +268,25 @@ __global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, f
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// arrive on `bar` once every cp.async this thread has issued so far has landed (the arrival is
+// counted against the barrier's expected count: .noinc)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ float lds_at(uint32_t addr) {
   float v;
@@ -352,9 +373,11 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 
 template <int S>
 __global__ void __launch_bounds__(kThreads, 1)
-fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int pitch, int Rr, int St, int resident0,
-           int nsteps, int nchunk, int items_cap, Ws ws, float* __restrict__ out) {
+fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int pitch, int St, int nblk, int nbk,
+           int nsteps, int items_cap, Ws ws, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxBlk];   // block b landed (every thread arrives through cp.async)
+  __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every warp is past bucket j
   __shared__ int s_ctr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y;
@@ -364,15 +387,20 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
   constexpr int bins = kP * kP;
   const int nb = nsteps + 1;
   const int row_words = kCh * pitch;
-  const int32_t* bstart = ws.bucket_start + (size_t)f * (nb + 2);
-  const float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
+  const int Rr = St * nblk;
   const float* fbase = feat + ((size_t)f * C + c0) * H * W;
   // dynamic shared: [record slots][staging tiles][ring]
   float4* slot = reinterpret_cast<float4*>(smem) + (size_t)warp * kRecVec;
   float* stage = smem + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * kCh * kP;
   float* ring = smem + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * kCh * kP + 16;
-  const uint32_t lane_base = smem_u32(ring) + (uint32_t)lane * (uint32_t)pitch * 4u;
-  if (tid == 0) s_ctr = 0;
+  const uint32_t ring_s = smem_u32(ring);
+  if (tid == 0) {
+    s_ctr = 0;
+    for (int i = 0; i < nblk; ++i) {
+      mbar_init(&full_bar[i], kThreads);
+      mbar_init(&done_bar[i], kWarps);
+    }
+  }
   // pad columns x in [W, pitch) stay zero for the whole kernel (clamped / invalid taps read them)
   {
     const int padw = pitch - W;
@@ -381,6 +409,7 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
       ring[(size_t)rc * pitch + x] = 0.0f;
     }
   }
+  __syncthreads();
 
   // output scatter pattern of this lane: flat index lane + 32*j of a [32][7] tile -> channel c_j
   int ooff[kP];
@@ -392,36 +421,9 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     ooff[j] = idx + c * (bins - kP);
     if (c < nch) omask |= 1u << j;
   }
-
-  for (int pr = warp; pr < kCh * resident0; pr += kWarps) {
-    const int c = pr & 31, y = pr >> 5;
-    if (c < nch) {
-      const float* src = fbase + ((size_t)c * H + y) * W;
-      float* dst = ring + (size_t)y * row_words + (size_t)c * pitch;
-      for (int x = lane; x < W; x += 32) dst[x] = __ldg(src + x);
-    }
-  }
-  __syncthreads();
-
-  // loader pairs of this warp: pair pr = warp + 12 j -> channel pr & 31, then (row dy, 128-column chunk)
-  int src_rel[kPairs];        // element offset of the pair's first column from row p0 of channel 0
-  uint32_t dst_rel[kPairs];   // byte offset from the first slot of the block
-  int dy_of[kPairs];
-  unsigned xmask = 0u;        // bit j * 4 + xi: column in range and channel present
-#pragma unroll
-  for (int j = 0; j < kPairs; ++j) {
-    const int pr = warp + j * kWarps;
-    const int c = pr & 31, t = pr >> 5;
-    const int dy = t / nchunk, ch = t - dy * nchunk;
-    const int x0 = ch * (32 * kXI) + lane;
-    dy_of[j] = (dy < St && c < nch) ? dy : (1 << 20);
-    src_rel[j] = (c * H + dy) * W + x0;
-    dst_rel[j] = (uint32_t)(((dy * kCh + c) * pitch + x0) * 4);
-#pragma unroll
-    for (int xi = 0; xi < kXI; ++xi)
-      if (x0 + 32 * xi < W) xmask |= 1u << (j * kXI + xi);
-  }
-  const uint32_t ring_s = smem_u32(ring);
+  const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)pitch * 4u;
+  const float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
+  const int n_items = ws.bucket_start[(size_t)f * (nb + 2) + nb];
 
   // work claiming: item index = part + split * (shared counter)
   auto claim = [&]() -> int {
@@ -430,78 +432,109 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     v = __shfl_sync(0xffffffffu, v, 0);
     return part + split * v;
   };
-  const int n_items = bstart[nb];
+  // ---------------- ring fill, cooperative: no producer warp.  Block b (St rows) may be written once
+  // every warp has released bucket b - nblk.  Each warp issues ITS share of a block (channel-row
+  // pairs warp, warp + 12, ...) as 4-byte cp.async and arrives on full_bar through them; it does so
+  // whenever it looks (item boundaries and every wait loop), so loads never depend on a warp that
+  // is itself waiting.  One warp cannot keep enough cp.async in flight to feed the SM; twelve can.
+  int issued = 0;       // blocks whose share this warp has issued
+  auto pump = [&]() {
+    while (issued < nsteps) {
+      const int b = issued;
+      if (b >= nblk && !mbar_test(&done_bar[b % nblk], (uint32_t)(((b - nblk) / nblk) & 1))) break;
+      const int y0 = b * St;
+      const int prow = min(H, y0 + St) - y0;
+      const uint32_t blk = ring_s + (uint32_t)((b % nblk) * St) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u;
+      const float* src0 = fbase + (size_t)y0 * W + lane;
+      for (int pr = warp; pr < kCh * prow; pr += kWarps) {
+        const int c = pr & 31, dy = pr >> 5;
+        if (c >= nch) continue;
+        const float* src = src0 + ((size_t)c * H + dy) * W;
+        const uint32_t dst = blk + (uint32_t)((dy * kCh + c) * pitch) * 4u;
+        for (int x = lane, o = 0; x < W; x += 32, o += 32) cp_async4(dst + 4u * o, src + o);
+      }
+      cp_async_arrive(&full_bar[b % nblk]);
+      ++issued;
+    }
+  };
+  auto wait_on = [&](uint64_t* bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) pump();
+  };
+  int cur = 0;          // buckets < cur are released by this warp
+  int landed = 0;       // blocks < landed have been observed in the ring by this warp
+  auto observe = [&](int upto) {
+    for (; landed < upto; ++landed) wait_on(&full_bar[landed % nblk], (uint32_t)((landed / nblk) & 1));
+  };
+  // mbarrier parity waits are only meaningful within one phase of the barrier's current phase, so
+  // every warp walks both barrier arrays strictly in order: it observes block j before it releases
+  // bucket j (block j + nblk cannot land before that release, so full_bar is never two phases
+  // ahead), and before arriving for bucket j it waits for the phase of bucket j - nblk (a warp that
+  // skips far ahead on a sparse frame would otherwise be counted twice in that older phase).
+  auto release = [&](int to) {
+    for (int j = cur; j < to; ++j) {
+      observe(j + 1);
+      if (j >= nblk) wait_on(&done_bar[j % nblk], (uint32_t)(((j - nblk) / nblk) & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done_bar[j % nblk]);
+    }
+    cur = max(cur, to);
+  };
+  pump();
   int pending = claim();
   float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pending < n_items) rec_next = __ldg(recs + (size_t)pending * kRecVec + lane);
-
-  int p0 = resident0, slot0 = resident0 % Rr;
-  for (int k = 0; k <= nsteps; ++k) {
-    const bool ring_step = k < nsteps;
-    const int prow = ring_step ? min(H, p0 + St) - p0 : 0;
-    if (prow > 0) {
-      // rows [p0, p0 + prow) go straight into the slots of rows that died with bucket k - 1
-      const float* src0 = fbase + (size_t)p0 * W;
-      const uint32_t blk = ring_s + (uint32_t)slot0 * (uint32_t)(row_words * 4);
-#pragma unroll
-      for (int j = 0; j < kPairs; ++j) {
-        const bool on = dy_of[j] < prow;
-#pragma unroll
-        for (int xi = 0; xi < kXI; ++xi)
-          if (on && (xmask & (1u << (j * kXI + xi)))) cp_async4(blk + dst_rel[j] + 128u * xi, src0 + src_rel[j] + 32 * xi);
+  while (pending < n_items) {
+    pump();
+    slot[lane] = rec_next;
+    __syncwarp();
+    const int nxt = claim();
+    if (nxt < n_items) rec_next = __ldg(recs + (size_t)nxt * kRecVec + lane);
+    const float4 hdr = slot[0];
+    const int r = __float_as_int(hdr.x), code = __float_as_int(hdr.y), bucket = __float_as_int(hdr.z);
+    const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
+    float* o = out + ((size_t)r * C + c0) * bins + ph0 * kP;
+    if (!(code >> 16)) {
+      // release the buckets this warp has left behind, then make sure the item's blocks have landed
+      release(bucket);
+      observe(min(bucket + nbk, nsteps));
+      switch (nph) {
+        case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 3: run_item<3, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 4: run_item<4, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 5: run_item<5, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
       }
-    }
-    const int i1 = bstart[k + 1];
-    while (pending < i1) {
-      slot[lane] = rec_next;
-      __syncwarp();
-      const int nxt = claim();
-      if (nxt < n_items) rec_next = __ldg(recs + (size_t)nxt * kRecVec + lane);
-      const float4 hdr = slot[0];
-      const int r = __float_as_int(hdr.x), code = __float_as_int(hdr.y);
-      const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
-      float* o = out + ((size_t)r * C + c0) * bins + ph0 * kP;
-      if (!(code >> 16)) {
-        switch (nph) {
-          case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          case 3: run_item<3, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          case 4: run_item<4, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          case 5: run_item<5, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-          default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        }
-      } else {
-        // bin-row taller than the resident window: taps straight from global memory (rare)
-        const bool ch_ok = lane < nch;
-        const float* roi = L.rois + (size_t)r * 5;
-        const float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
-        const RoiGeom g = roi_geometry(rr, ws.scale, kP, kP, S, ws.aligned != 0);
-        const float* plane = fbase + (size_t)(ch_ok ? lane : 0) * H * W;
-        for (int pw = 0; pw < kP; ++pw) {
-          float acc = 0.0f;
-          for (int iy = 0; iy < S; ++iy) {
-            const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph0, iy, S, H);
-            for (int ix = 0; ix < S; ++ix) {
-              const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, S, W);
-              if (!(ty.ok && tx.ok)) continue;
-              const float top = tx.wlo * __ldg(plane + ty.lo * W + tx.lo) + tx.whi * __ldg(plane + ty.lo * W + tx.hi);
-              const float bot = tx.wlo * __ldg(plane + ty.hi * W + tx.lo) + tx.whi * __ldg(plane + ty.hi * W + tx.hi);
-              acc += ty.wlo * top + ty.whi * bot;
-            }
+    } else {
+      // bin-row taller than the resident window: taps straight from global memory (rare)
+      const bool ch_ok = lane < nch;
+      const float* roi = L.rois + (size_t)r * 5;
+      const float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
+      const RoiGeom g = roi_geometry(rr, ws.scale, kP, kP, S, ws.aligned != 0);
+      const float* plane = fbase + (size_t)(ch_ok ? lane : 0) * H * W;
+      for (int pw = 0; pw < kP; ++pw) {
+        float acc = 0.0f;
+        for (int iy = 0; iy < S; ++iy) {
+          const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph0, iy, S, H);
+          for (int ix = 0; ix < S; ++ix) {
+            const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, S, W);
+            if (!(ty.ok && tx.ok)) continue;
+            const float top = tx.wlo * __ldg(plane + ty.lo * W + tx.lo) + tx.whi * __ldg(plane + ty.lo * W + tx.hi);
+            const float bot = tx.wlo * __ldg(plane + ty.hi * W + tx.lo) + tx.whi * __ldg(plane + ty.hi * W + tx.hi);
+            acc += ty.wlo * top + ty.whi * bot;
           }
-          if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
         }
+        if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
       }
-      __syncwarp();
-      pending = nxt;
     }
-    if (prow > 0) cp_async_wait_all();
-    p0 += prow;
-    slot0 += prow;
-    if (slot0 >= Rr) slot0 -= Rr;
-    if (ring_step) __syncthreads();
+    __syncwarp();
+    pending = nxt;
   }
+  // out of items: release every remaining bucket so the producer can finish
+  release(nsteps);
+  while (issued < nsteps) pump();
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 }  // namespace rows
@@ -538,8 +571,8 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
                                                           p.nsteps, p.row_bytes, items_cap, ws);                  \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));     \
-    fwd_kernel<SS><<<grid, kThreads, p.smem, st>>>(feat, L, C, H, W, p.pitch, p.Rr, p.St, p.resident0, p.nsteps,  \
-                                                   p.nchunk, items_cap, ws, out);                                 \
+    fwd_kernel<SS><<<grid, kThreads, p.smem, st>>>(feat, L, C, H, W, p.pitch, p.St, p.nblk, p.nbk, p.nsteps,      \
+                                                   items_cap, ws, out);                                           \
     B2D_LAUNCHED();                                                                                               \
   } while (0)
   if (S == 2) B2D_ROWS(2);
