@@ -16,21 +16,47 @@
 //     accumulators with that row's weights: acc[p][pw] += wy[row][p] * T[pw].
 //     A 5x5-pixel RoI costs 5 rows x 28 taps = 140 wavefronts instead of 784; only RoIs whose bins
 //     are taller than two pixels still pay 16 taps per output (their samples share nothing).
-//   * tap addresses are [column register + uniform row register + imm]: the row offset is made
-//     warp-uniform with one CREDUX per row, so the inner loop has no address arithmetic at all.
 //
-// Data flow per CTA = (32-channel group, frame[, item split]): the CTA sweeps the feature rows top
-// to bottom through a ring [slot][channel][pitch] (pitch = 1 mod 32 words, so 32 lanes reading the
-// same pixel of 32 channels never conflict); rows of the next step are prefetched into registers
-// while the current step computes, so every feature byte is read from HBM/L2 once per channel
-// group.  A prep kernel turns the RoIs of a frame into self-contained item records bucketed by
-// first row; warps claim items from a shared counter (dynamic balancing) and prefetch the next
-// record while they compute.
+// Data flow per CTA = (32-channel group, frame[, item split]).  The CTA streams the feature rows of
+// its 32 channels top to bottom through a ring of nblk blocks of St rows.  Lane c reads pixel
+// (row, x) of channel c at word  slot*row_words + c*lane_stride + x  with lane_stride = 1 (mod 32),
+// so the 32 lanes of a tap always hit 32 different banks.
+//
+//   * TMA fill (W % 4 == 0): one producer warp.  Bulk TMA lands rows at 16-byte granularity, which
+//     would put channels c and c+8 on the same banks (and tiled-TMA box coordinates must be 16-byte
+//     aligned too: a per-channel element skew raises an illegal-instruction fault), so the rows are
+//     first pulled into a small dense staging buffer [32 ch][W] by 1-D bulk copies (one per channel
+//     row, several rows in flight, no registers, no issue slots) and the producer then repacks a
+//     staged row into its skewed ring slot with conflict-free LDS/STS - 2 wavefronts per 32
+//     elements, 3 % of the shared-memory budget.  (Register-staged LDG producers stall on address
+//     register reuse with only 6 scoreboards per warp; 4-byte cp.async from one warp sustains only
+//     ~8 copies in flight.)
+//   * cp.async fill (other shapes): every warp issues its share of a block as 4-byte LDGSTS whenever
+//     it looks (item boundaries and wait loops).
+//
+// Blocks are handed over with mbarriers only (full[b]: block landed, done[j]: every consumer warp
+// has left bucket j), there is no CTA-wide barrier after start-up: bucket k may touch blocks
+// k .. k+nbk-1 and the remaining nblk-nbk blocks are slack, so warps drift apart by that many
+// blocks.  A prep kernel turns the RoIs of a frame into self-contained item records sorted by first
+// row; warps claim items from a shared counter and prefetch the next record while they compute.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "roi_common.cuh"
 
 namespace b2d {
 
 namespace rows {
+
+#ifdef B2D_ROWS_TIMING
+__device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait done, [3] run_item, [4] items, [5] producer wait done, [6] producer wait stg, [7] producer total
+#define DBG_T0(v) long long v = clock64()
+#define DBG_ACC(slot, v) dbg_acc[slot] += clock64() - v
+#else
+#define DBG_T0(v)
+#define DBG_ACC(slot, v)
+#endif
 
 constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
@@ -38,31 +64,34 @@ constexpr int kCh = 32;            // channels per CTA (lanes)
 constexpr int kP = 7;              // PH = PW = 7
 constexpr int kRecVec = 32;        // float4 per item record
 constexpr int kRecBytes = kRecVec * 16;
-constexpr int kMaxRows = 12;       // distinct feature rows per item
-constexpr int kXVec = 7;           // float4 of column taps {xo_a, lx_a, xo_b, lx_b}
+constexpr int kMaxRows = 10;       // distinct feature rows per item
+constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 
-// Ring geometry.  The ring holds nblk blocks of St rows.  Bucket k (items whose first row lies in
-// block k) may touch blocks k .. k + nbk - 1; the other nblk - nbk blocks are slack: they are being
-// refilled while slower warps still work on older buckets, so warps drift apart by up to that many
-// blocks instead of meeting at a barrier every step.
+constexpr int kStages = 3;         // staging rows of the TMA fill
+
 struct Plan {
-  int pitch;      // words per (slot, channel) row, = 1 mod 32 and > W
-  int row_bytes;  // bytes per ring slot
+  int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
+  int lane_stride;  // words between channels of one slot (= 1 mod 32)
+  int row_words;    // words per ring slot
   int Rr, St, nblk, nbk, span_max, nsteps;
   size_t smem;
   bool ok;
 };
 
-static Plan make_plan(int H, int W) {
+static Plan make_plan(int H, int W, bool allow_tma) {
   Plan p{};
-  p.pitch = ((W + 1 + 30) / 32) * 32 + 1;            // smallest value = 1 (mod 32) that is >= W + 1
-  p.row_bytes = kCh * p.pitch * 4;
-  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * kCh * kP * 4 + 64;
-  const size_t budget = 227 * 1024 - 2048 - fixed;
-  int Rr = (int)(budget / p.row_bytes);
-  if (Rr < 6) { p.ok = false; return p; }
+  p.fill = (allow_tma && W % 4 == 0) ? 1 : 0;
+  const int pitch = ((W + 1 + 30) / 32) * 32 + 1;    // smallest value = 1 (mod 32) that is >= W + 1
+  p.lane_stride = pitch;
+  p.row_words = kCh * pitch;
+  const size_t row_bytes = (size_t)p.row_words * 4;
+  const size_t staging = p.fill ? (size_t)kStages * kCh * W * 4 : 0;
+  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * kCh * kP * 4 + 256 + staging;
+  const size_t budget = 227 * 1024 - 2048;
+  if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
+  int Rr = (int)((budget - fixed) / row_bytes);
   if (Rr >= H) {
     p.Rr = H; p.St = H; p.nblk = 1; p.nbk = 1; p.span_max = H; p.nsteps = 1;
   } else {
@@ -76,7 +105,7 @@ static Plan make_plan(int H, int W) {
     p.nsteps = ceil_div(H, St);
   }
   if (p.span_max > kMaxRows) p.span_max = kMaxRows;
-  p.smem = fixed + (size_t)p.Rr * p.row_bytes;
+  p.smem = fixed + (size_t)p.Rr * row_bytes;
   p.ok = p.span_max >= 4 && p.nblk <= kMaxBlk;
   return p;
 }
@@ -138,6 +167,11 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
   if (a < kP) emit(a, kP - a, cf, cl, false);
 }
 
+// Record of one item (float4 units):
+//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16, bucket, -}
+//   [1..11]   14 column taps x 3 words {byte offset of the lo column, hx, lx}; the hi column is lo + 1
+//   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 3);
+//             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
 template <int S>
 __global__ void __launch_bounds__(256)
 prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int nsteps,
@@ -194,26 +228,25 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     for_each_item<S>(g, H, span_max, [&](int ph0, int nph, int cf, int cl, bool slow) {
       const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
       float4* rec = recs + (size_t)(offs[b] + atomicAdd(&fill[b], 1)) * kRecVec;
-      // column taps: {byte offset of the lo column, weight of the hi column}; the hi column is lo + 1.
-      // Invalid samples and the clamped right border point at / run into the zero pad column W.
-      for (int v = 0; v < kXVec; ++v) {
-        float q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int h = 0; h < 2; ++h) {
-          const int k = 2 * v + h;                       // column slot: pw = k / 2, ix = k % 2 (S == 2)
-          int xo = W * 4;
-          float lx = 0.0f;
-          if (k < kP * S) {
-            const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
-            if (t.ok) {
-              xo = t.lo * 4;
-              lx = t.whi;
-            }
+      // column taps.  Invalid samples carry zero weights and point at column 0 (always resident);
+      // at the clamped right border lx is 0 and the hi tap reads whatever follows the row (finite).
+      float* xw = reinterpret_cast<float*>(rec + 1);
+      for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
+        int xo = 0;
+        float hx = 0.0f, lx = 0.0f;
+        if (k < kP * S) {
+          const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
+          if (t.ok) {
+            xo = t.lo * 4;
+            hx = t.wlo;
+            lx = t.whi;
           }
-          q[2 * h] = __int_as_float(xo);
-          q[2 * h + 1] = lx;
         }
-        rec[1 + v] = make_float4(q[0], q[1], q[2], q[3]);
+        xw[3 * k] = __int_as_float(xo);
+        xw[3 * k + 1] = hx;
+        xw[3 * k + 2] = lx;
       }
+      xw[42] = xw[43] = 0.0f;
       // distinct feature rows of the item and their weights per bin-row
       int nrows = 0;
       if (!slow) {
@@ -262,9 +295,7 @@ __global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, f
 }
 
 // ------------------------------------------------------------------------------------------
-// 4-byte asynchronous copy global -> shared (LDGSTS): the ring layout interleaves channels at word
-// granularity, so neither 16-byte cp.async nor bulk TMA can write it; 4-byte copies keep the fill
-// off the register file and off the issue slots of the compute code.
+// 4-byte asynchronous copy global -> shared (LDGSTS), the fill of the non-TMA path.
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -287,6 +318,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// tiled 2-D bulk tensor copy global -> shared, completion counted in bytes on `bar`
+// (box coordinates must be 16-byte aligned in the innermost dimension)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
 
 __device__ __forceinline__ float lds_at(uint32_t addr) {
   float v;
@@ -303,18 +342,21 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
   constexpr int RV = NPH > 3 ? 2 : 1;
   uint32_t xa[NX];
   float lx[NX], hx[NX];
+  {
+    float q[4 * kXVec];
 #pragma unroll
-  for (int v = 0; v < kXVec; ++v) {
-    const float4 q = slot[1 + v];
-    if (2 * v < NX) {
-      xa[2 * v] = lane_base + (uint32_t)__float_as_int(q.x);
-      lx[2 * v] = q.y;
-      hx[2 * v] = 1.0f - q.y;
+    for (int v = 0; v < kXVec; ++v) {
+      const float4 t = slot[1 + v];
+      q[4 * v] = t.x;
+      q[4 * v + 1] = t.y;
+      q[4 * v + 2] = t.z;
+      q[4 * v + 3] = t.w;
     }
-    if (2 * v + 1 < NX) {
-      xa[2 * v + 1] = lane_base + (uint32_t)__float_as_int(q.z);
-      lx[2 * v + 1] = q.w;
-      hx[2 * v + 1] = 1.0f - q.w;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+      xa[k] = lane_base + (uint32_t)__float_as_int(q[3 * k]);
+      hx[k] = q[3 * k + 1];
+      lx[k] = q[3 * k + 2];
     }
   }
   float acc[NPH][kP];
@@ -337,7 +379,7 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       wy[6] = e1.w;
     }
     // the row offset is the same in every lane; the reduction tells ptxas so (CREDUX -> uniform
-    // register), which lets every tap below use [column + uniform row + imm] addressing
+    // register), which lets the taps below use [column + uniform row + imm] addressing
     const uint32_t ro = __reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(e0.x));
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
@@ -371,46 +413,137 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
   }
 }
 
-template <int S>
+struct KArgs {
+  const float* feat;
+  RoiList L;
+  int C, H, W;
+  int lane_stride, row_words;
+  int St, nblk, nbk, nsteps, items_cap, nostore;
+  Ws ws;
+  float* out;
+};
+
+template <int S, bool FILL>
 __global__ void __launch_bounds__(kThreads, 1)
-fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int pitch, int St, int nblk, int nbk,
-           int nsteps, int items_cap, Ws ws, float* __restrict__ out) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxBlk];   // block b landed (every thread arrives through cp.async)
-  __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every warp is past bucket j
+fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxBlk];   // block b landed
+  __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every consumer warp is past bucket j
+  __shared__ __align__(8) uint64_t stg_bar[kStages];    // staging row landed (TMA bytes)
   __shared__ int s_ctr;
+  constexpr int kConsumers = FILL ? kWarps - 1 : kWarps;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * kCh;
+  const int C = a.C, H = a.H, W = a.W;
   const int nch = min(kCh, C - c0);
   const int split = gridDim.z, part = blockIdx.z;
   constexpr int bins = kP * kP;
+  const int St = a.St, nblk = a.nblk, nbk = a.nbk, nsteps = a.nsteps;
   const int nb = nsteps + 1;
-  const int row_words = kCh * pitch;
-  const int Rr = St * nblk;
-  const float* fbase = feat + ((size_t)f * C + c0) * H * W;
-  // dynamic shared: [record slots][staging tiles][ring]
-  float4* slot = reinterpret_cast<float4*>(smem) + (size_t)warp * kRecVec;
-  float* stage = smem + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * kCh * kP;
-  float* ring = smem + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * kCh * kP + 16;
+  const int row_words = a.row_words;
+  const float* fbase = a.feat + ((size_t)f * C + c0) * H * W;
+  // dynamic shared: [ring (128-byte aligned)][record slots][staging tiles]
+  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);
+  float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * kCh * kP;
+  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * kCh * kP;
   const uint32_t ring_s = smem_u32(ring);
   if (tid == 0) {
     s_ctr = 0;
+    for (int i = 0; i < kStages; ++i) mbar_init(&stg_bar[i], 1);
     for (int i = 0; i < nblk; ++i) {
-      mbar_init(&full_bar[i], kThreads);
-      mbar_init(&done_bar[i], kWarps);
+      mbar_init(&full_bar[i], FILL ? 1 : kThreads);
+      mbar_init(&done_bar[i], kConsumers);
     }
   }
-  // pad columns x in [W, pitch) stay zero for the whole kernel (clamped / invalid taps read them)
   {
-    const int padw = pitch - W;
-    for (int i = tid; i < Rr * kCh * padw; i += kThreads) {
+    // pad columns x in [W, pitch) are read by clamped taps with weight 0: keep them finite
+    const int pitch = a.lane_stride, padw = pitch - W;
+    for (int i = tid; i < St * nblk * kCh * padw; i += kThreads) {
       const int rc = i / padw, x = W + (i - rc * padw);
       ring[(size_t)rc * pitch + x] = 0.0f;
     }
   }
   __syncthreads();
 
+  if (FILL && warp == kWarps - 1) {
+    // ---------------- producer: one tiled TMA per feature row (box = [32 planes][W]) into a dense
+    // staging buffer, then repack the staged row into its skewed ring slot
+#ifdef B2D_ROWS_TIMING
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    DBG_T0(tp);
+    const uint32_t row_tx = (uint32_t)kCh * (uint32_t)W * 4u;     // the box is always 32 planes (OOB planes zero-filled)
+    const int nchunk = (W + 31) / 32;
+    const bool tail_ok = lane + 32 * (nchunk - 1) < W;
+    const int plane0 = f * C + c0;
+    auto fetch = [&](int y) {        // row y of the 32 channels -> staging buffer y % kStages
+      if (lane == 0) {
+        uint64_t* bar = &stg_bar[y % kStages];
+        mbar_expect_tx(bar, row_tx);
+        tma_load_2d(smem_u32(stg + (size_t)(y % kStages) * kCh * W), &tmap, y * W, plane0, bar);
+      }
+    };
+    for (int y = 0; y < kStages && y < H; ++y) fetch(y);
+    for (int y = 0; y < H; ++y) {
+      const int b = y / St, dy = y - b * St;
+      {
+        DBG_T0(t1);
+        if (dy == 0 && b >= nblk) mbar_wait(&done_bar[(b - nblk) % nblk], (uint32_t)(((b - nblk) / nblk) & 1));
+        DBG_ACC(5, t1);
+      }
+      {
+        DBG_T0(t2);
+        mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
+        DBG_ACC(6, t2);
+      }
+      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * W) + (uint32_t)lane * 4u;
+      uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u;
+      const uint32_t sstep = (uint32_t)W * 4u, dstep = (uint32_t)a.lane_stride * 4u;
+      // 8 channels x up to 4 chunks (32 values) in flight per lane
+      for (int c8 = 0; c8 < nch; c8 += 8) {
+        for (int cg = 0; cg < nchunk; cg += 4) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ch = cg + k;
+              if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j * 4 + k]) : "r"(src + j * sstep + 128u * ch) : "memory");
+            }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ch = cg + k;
+              if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + j * dstep + 128u * ch), "f"(v[j * 4 + k]) : "memory");
+            }
+        }
+        src += 8 * sstep;
+        dst += 8 * dstep;
+      }
+      __syncwarp();
+      {
+        DBG_T0(t4);
+        if (y + kStages < H) fetch(y + kStages);     // this staging buffer is free again
+        DBG_ACC(4, t4);
+      }
+      if (dy == St - 1 || y == H - 1) {
+        if (lane == 0) mbar_arrive(&full_bar[b % nblk]);
+      }
+    }
+    DBG_ACC(7, tp);
+#ifdef B2D_ROWS_TIMING
+    if (lane == 0)
+      for (int i = 4; i < 8; ++i) atomicAdd(&g_dbg[i], (unsigned long long)dbg_acc[i]);
+#endif
+    return;
+  }
+
+  // ---------------- consumers
   // output scatter pattern of this lane: flat index lane + 32*j of a [32][7] tile -> channel c_j
   int ooff[kP];
   unsigned omask = 0u;
@@ -421,9 +554,10 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     ooff[j] = idx + c * (bins - kP);
     if (c < nch) omask |= 1u << j;
   }
-  const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)pitch * 4u;
-  const float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
-  const int n_items = ws.bucket_start[(size_t)f * (nb + 2) + nb];
+  if (a.nostore) omask = 0u;
+  const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)a.lane_stride * 4u;
+  const float4* recs = a.ws.records + (size_t)f * a.items_cap * kRecVec;
+  const int n_items = a.ws.bucket_start[(size_t)f * (nb + 2) + nb];
 
   // work claiming: item index = part + split * (shared counter)
   auto claim = [&]() -> int {
@@ -432,13 +566,15 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     v = __shfl_sync(0xffffffffu, v, 0);
     return part + split * v;
   };
-  // ---------------- ring fill, cooperative: no producer warp.  Block b (St rows) may be written once
-  // every warp has released bucket b - nblk.  Each warp issues ITS share of a block (channel-row
-  // pairs warp, warp + 12, ...) as 4-byte cp.async and arrives on full_bar through them; it does so
-  // whenever it looks (item boundaries and every wait loop), so loads never depend on a warp that
-  // is itself waiting.  One warp cannot keep enough cp.async in flight to feed the SM; twelve can.
+
+  // cp.async fill, cooperative: block b may be written once every warp has released bucket b - nblk.
+  // Each warp issues ITS share of a block (channel-row pairs warp, warp + 12, ...) and arrives on
+  // full_bar through the copies; it does so whenever it looks (item boundaries and every wait
+  // loop), so loads never depend on a warp that is itself waiting.  (One warp cannot keep enough
+  // LDGSTS in flight to feed the SM.)
   int issued = 0;       // blocks whose share this warp has issued
   auto pump = [&]() {
+    if (FILL) return;
     while (issued < nsteps) {
       const int b = issued;
       if (b >= nblk && !mbar_test(&done_bar[b % nblk], (uint32_t)(((b - nblk) / nblk) & 1))) break;
@@ -450,7 +586,7 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
         const int c = pr & 31, dy = pr >> 5;
         if (c >= nch) continue;
         const float* src = src0 + ((size_t)c * H + dy) * W;
-        const uint32_t dst = blk + (uint32_t)((dy * kCh + c) * pitch) * 4u;
+        const uint32_t dst = blk + (uint32_t)((dy * kCh + c) * a.lane_stride) * 4u;
         for (int x = lane, o = 0; x < W; x += 32, o += 32) cp_async4(dst + 4u * o, src + o);
       }
       cp_async_arrive(&full_bar[b % nblk]);
@@ -458,12 +594,22 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     }
   };
   auto wait_on = [&](uint64_t* bar, uint32_t parity) {
-    while (!mbar_test(bar, parity)) pump();
+    if (FILL) {
+      mbar_wait(bar, parity);
+    } else {
+      while (!mbar_test(bar, parity)) pump();
+    }
   };
   int cur = 0;          // buckets < cur are released by this warp
   int landed = 0;       // blocks < landed have been observed in the ring by this warp
+#ifdef B2D_ROWS_TIMING
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  DBG_T0(tc);
   auto observe = [&](int upto) {
+    DBG_T0(t1);
     for (; landed < upto; ++landed) wait_on(&full_bar[landed % nblk], (uint32_t)((landed / nblk) & 1));
+    DBG_ACC(1, t1);
   };
   // mbarrier parity waits are only meaningful within one phase of the barrier's current phase, so
   // every warp walks both barrier arrays strictly in order: it observes block j before it releases
@@ -473,7 +619,11 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
   auto release = [&](int to) {
     for (int j = cur; j < to; ++j) {
       observe(j + 1);
-      if (j >= nblk) wait_on(&done_bar[j % nblk], (uint32_t)(((j - nblk) / nblk) & 1));
+      {
+        DBG_T0(t2);
+        if (j >= nblk) wait_on(&done_bar[j % nblk], (uint32_t)(((j - nblk) / nblk) & 1));
+        DBG_ACC(2, t2);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&done_bar[j % nblk]);
     }
@@ -483,6 +633,7 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
   int pending = claim();
   float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pending < n_items) rec_next = __ldg(recs + (size_t)pending * kRecVec + lane);
+
   while (pending < n_items) {
     pump();
     slot[lane] = rec_next;
@@ -492,11 +643,12 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     const float4 hdr = slot[0];
     const int r = __float_as_int(hdr.x), code = __float_as_int(hdr.y), bucket = __float_as_int(hdr.z);
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
-    float* o = out + ((size_t)r * C + c0) * bins + ph0 * kP;
+    float* o = a.out + ((size_t)r * C + c0) * bins + ph0 * kP;
     if (!(code >> 16)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       release(bucket);
       observe(min(bucket + nbk, nsteps));
+      DBG_T0(t3);
       switch (nph) {
         case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
         case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
@@ -506,12 +658,16 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
         case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
         default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
       }
+      DBG_ACC(3, t3);
+#ifdef B2D_ROWS_TIMING
+      dbg_acc[4] += 0;
+#endif
     } else {
       // bin-row taller than the resident window: taps straight from global memory (rare)
       const bool ch_ok = lane < nch;
-      const float* roi = L.rois + (size_t)r * 5;
+      const float* roi = a.L.rois + (size_t)r * 5;
       const float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
-      const RoiGeom g = roi_geometry(rr, ws.scale, kP, kP, S, ws.aligned != 0);
+      const RoiGeom g = roi_geometry(rr, a.ws.scale, kP, kP, S, a.ws.aligned != 0);
       const float* plane = fbase + (size_t)(ch_ok ? lane : 0) * H * W;
       for (int pw = 0; pw < kP; ++pw) {
         float acc = 0.0f;
@@ -531,13 +687,60 @@ fwd_kernel(const float* __restrict__ feat, RoiList L, int C, int H, int W, int p
     __syncwarp();
     pending = nxt;
   }
-  // out of items: release every remaining bucket so the producer can finish
+  // out of items: release every remaining bucket so the fill can finish
+  DBG_ACC(0, tc);
+#ifdef B2D_ROWS_TIMING
+  if (lane == 0)
+    for (int i = 0; i < 5; ++i) atomicAdd(&g_dbg[i], (unsigned long long)dbg_acc[i]);
+#endif
   release(nsteps);
-  while (issued < nsteps) pump();
-  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (!FILL) {
+    while (issued < nsteps) pump();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// feature planes as a 2-D tensor [F*C planes][H*W elements]; box = one row of 32 consecutive planes
+static bool make_tmap(CUtensorMap* map, const float* feat, int F, int C, int H, int W) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (reinterpret_cast<uintptr_t>(feat) & 15u) || W % 4 != 0 || W > 256) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)H * W, (cuuint64_t)F * C};
+  const cuuint64_t strides[1] = {(cuuint64_t)H * W * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)kCh};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace rows
+
+#ifdef B2D_ROWS_TIMING
+extern "C" void b2d_rows_debug(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, rows::g_dbg, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(rows::g_dbg, z, sizeof(z));
+  }
+}
+#endif
 
 size_t rows_workspace_bytes(int F, int H, int per_frame) { return rows::carve(nullptr, F, per_frame, H).bytes; }
 
@@ -547,7 +750,10 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
                            cudaStream_t st) {
   using namespace rows;
   if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 27)) return B2D_ERR_UNSUPPORTED;
-  const Plan p = make_plan(H, W);
+  static const bool coop = getenv("B2D_ROWS_COOP_FILL") != nullptr;   // debugging knob: force the cp.async fill
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const Plan p = make_plan(H, W, !coop && make_tmap(&tmap, feat, F, C, H, W));
   if (!p.ok) return B2D_ERR_UNSUPPORTED;
   const int per_frame = L.seg_count ? L.seg_stride : L.n;
   Ws ws = carve(workspace, F, per_frame, H);
@@ -565,18 +771,24 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   while (split < 4 && groups * split < 2 * kNumSMs) split *= 2;
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
-#define B2D_ROWS(SS)                                                                                              \
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
+#define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
     prep_kernel<SS><<<F, 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max,        \
-                                                          p.nsteps, p.row_bytes, items_cap, ws);                  \
+                                                          p.nsteps, p.row_words * 4, items_cap, ws);              \
     B2D_LAUNCHED();                                                                                               \
-    B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));     \
-    fwd_kernel<SS><<<grid, kThreads, p.smem, st>>>(feat, L, C, H, W, p.pitch, p.St, p.nblk, p.nbk, p.nsteps,      \
-                                                   items_cap, ws, out);                                           \
+    B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
+    fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap);                                                  \
     B2D_LAUNCHED();                                                                                               \
   } while (0)
-  if (S == 2) B2D_ROWS(2);
-  else B2D_ROWS(1);
+#define B2D_ROWS_S(FF)           \
+  do {                           \
+    if (S == 2) B2D_ROWS(2, FF); \
+    else B2D_ROWS(1, FF);        \
+  } while (0)
+  if (p.fill) B2D_ROWS_S(true);
+  else B2D_ROWS_S(false);
+#undef B2D_ROWS_S
 #undef B2D_ROWS
   return B2D_OK;
 }
