@@ -10,7 +10,7 @@ anchors, _ = generate_anchors_pre(cfg["Hf"], cfg["Wf"], cfg["stride"], bench.SCA
 prob, deltas, feat, info = bench.synth_frames(cfg, F, dev, 0)
 rois, scores, _, _, num = ops.proposal_batched(prob, deltas, info, anchors, None, cfg["A"], cfg["pre_nms"], cfg["post_nms"], cfg["nms_thresh"], batch_index_stride=1)
 pooled = torch.empty(F * 300, 1024, 7, 7, device=dev)
-out = (ctypes.c_ulonglong * 8)()
+out = (ctypes.c_ulonglong * 16)()
 for it in range(3):
     L.b2d_rows_debug(out, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -20,4 +20,4 @@ for it in range(3):
     L.b2d_rows_debug(out, 0)
     v = list(out)
     ncons = 11 * 32 * F
-    print(f"ms {e0.elapsed_time(e1):.3f} per consumer-warp avg cycles: total {v[0]/ncons:.0f} wait_full {v[1]/ncons:.0f} wait_done {v[2]/ncons:.0f} run_item {v[3]/ncons:.0f} fetch(prod) {v[4]/(32*F):.0f} | producer: total {v[7]/(32*F):.0f} wait_done {v[5]/(32*F):.0f} wait_stg {v[6]/(32*F):.0f}")
+    print(f"ms {e0.elapsed_time(e1):.3f} per consumer-warp avg cycles: total {v[0]/ncons:.0f} wait_full {v[1]/ncons:.0f} wait_done {v[2]/ncons:.0f} run_item {v[3]/ncons:.0f} fetch(prod) {v[4]/(32*F):.0f} ri_setup {v[8]/ncons:.0f} ri_rows {v[9]/ncons:.0f} ri_out {v[10]/ncons:.0f} | producer: total {v[7]/(32*F):.0f} wait_done {v[5]/(32*F):.0f} wait_stg {v[6]/(32*F):.0f}")

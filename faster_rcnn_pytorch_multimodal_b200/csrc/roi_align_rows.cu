@@ -69,7 +69,7 @@ constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 
-constexpr int kStages = 3;         // staging rows of the TMA fill
+constexpr int kStages = 2;         // staging rows of the TMA fill
 
 struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
@@ -88,7 +88,7 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   p.row_words = kCh * pitch;
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * W * 4 : 0;
-  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * kCh * kP * 4 + 256 + staging;
+  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * 2 * kCh * kP * 4 + 256 + staging;
   const size_t budget = 227 * 1024 - 2048;
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
@@ -365,14 +365,15 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) acc[p][pw] = 0.0f;
 
+  // row entries are fetched one row ahead so that the LDS -> CREDUX -> tap-address chain of row i + 1
+  // overlaps the taps of row i (reading one entry past the last row stays inside shared memory)
+  float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + (RV == 2 ? 1 : 0)];
   for (int i = 0; i < nrows; ++i) {
-    const float4 e0 = slot[kRowVec0 + i * RV];
     float wy[kP];
     wy[0] = e0.y;
     wy[1] = e0.z;
     wy[2] = e0.w;
     if (RV == 2) {
-      const float4 e1 = slot[kRowVec0 + i * RV + 1];
       wy[3] = e1.x;
       wy[4] = e1.y;
       wy[5] = e1.z;
@@ -381,6 +382,8 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
     // the row offset is the same in every lane; the reduction tells ptxas so (CREDUX -> uniform
     // register), which lets the taps below use [column + uniform row + imm] addressing
     const uint32_t ro = __reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(e0.x));
+    e0 = slot[kRowVec0 + (i + 1) * RV];
+    if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
       float t;
@@ -400,17 +403,19 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       for (int p = 0; p < NPH; ++p) acc[p][pw] = fmaf(wy[p], t, acc[p][pw]);
     }
   }
-  // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw)
+  // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw); two
+  // tiles alternate, so the shared-memory round trip of bin-row p overlaps the staging of p + 1
 #pragma unroll
   for (int p = 0; p < NPH; ++p) {
+    float* tile = stage + (p & 1) * (kCh * kP);
 #pragma unroll
-    for (int pw = 0; pw < kP; ++pw) stage[lane * kP + pw] = acc[p][pw];
+    for (int pw = 0; pw < kP; ++pw) tile[lane * kP + pw] = acc[p][pw];
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kP; ++j)
-      if (omask & (1u << j)) o[p * kP + ooff[j]] = stage[lane + 32 * j];
-    __syncwarp();
+      if (omask & (1u << j)) o[p * kP + ooff[j]] = tile[lane + 32 * j];
   }
+  __syncwarp();
 }
 
 struct KArgs {
@@ -425,12 +430,14 @@ struct KArgs {
 
 template <int S, bool FILL>
 __global__ void __launch_bounds__(kThreads, 1)
-fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap tmap) {
+fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap tmap, const float* __restrict__ feat_g,
+           const float4* __restrict__ records_g, const float* __restrict__ rois_g, float* __restrict__ out_g) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxBlk];   // block b landed
   __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every consumer warp is past bucket j
   __shared__ __align__(8) uint64_t stg_bar[kStages];    // staging row landed (TMA bytes)
   __shared__ int s_ctr;
+  __shared__ int s_progress[kWarps];                    // TMA fill: bucket each consumer warp is working in
   constexpr int kConsumers = FILL ? kWarps - 1 : kWarps;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y;
@@ -442,13 +449,14 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const int St = a.St, nblk = a.nblk, nbk = a.nbk, nsteps = a.nsteps;
   const int nb = nsteps + 1;
   const int row_words = a.row_words;
-  const float* fbase = a.feat + ((size_t)f * C + c0) * H * W;
+  const float* fbase = feat_g + ((size_t)f * C + c0) * H * W;
   // dynamic shared: [ring (128-byte aligned)][record slots][staging tiles]
   float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
-  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * kCh * kP;
-  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * kCh * kP;
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * 2 * kCh * kP;
+  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * 2 * kCh * kP;
   const uint32_t ring_s = smem_u32(ring);
+  if (tid < kWarps) s_progress[tid] = 0;
   if (tid == 0) {
     s_ctr = 0;
     for (int i = 0; i < kStages; ++i) mbar_init(&stg_bar[i], 1);
@@ -490,7 +498,15 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       const int b = y / St, dy = y - b * St;
       {
         DBG_T0(t1);
-        if (dy == 0 && b >= nblk) mbar_wait(&done_bar[(b - nblk) % nblk], (uint32_t)(((b - nblk) / nblk) & 1));
+        if (dy == 0 && b >= nblk) {
+          // the slot is free once every consumer warp works in a bucket beyond b - nblk
+          for (;;) {
+            int pr = lane < kConsumers ? *reinterpret_cast<volatile int*>(&s_progress[lane]) : 0x7fffffff;
+            pr = (int)__reduce_min_sync(0xffffffffu, (unsigned)pr);
+            if (pr > b - nblk) break;
+            __nanosleep(64);
+          }
+        }
         DBG_ACC(5, t1);
       }
       {
@@ -556,15 +572,15 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   }
   if (a.nostore) omask = 0u;
   const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)a.lane_stride * 4u;
-  const float4* recs = a.ws.records + (size_t)f * a.items_cap * kRecVec;
-  const int n_items = a.ws.bucket_start[(size_t)f * (nb + 2) + nb];
+  const float4* recs = records_g + (size_t)f * a.items_cap * kRecVec;
+  const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.bucket_start[(size_t)f * (nb + 2) + nb]);
 
   // work claiming: item index = part + split * (shared counter)
   auto claim = [&]() -> int {
-    int v = 0;
-    if (lane == 0) v = atomicAdd(&s_ctr, 1);
-    v = __shfl_sync(0xffffffffu, v, 0);
-    return part + split * v;
+    unsigned v = 0;
+    if (lane == 0) v = (unsigned)atomicAdd(&s_ctr, 1);
+    v = __reduce_max_sync(0xffffffffu, v);        // broadcast that ptxas knows to be uniform
+    return part + split * (int)v;
   };
 
   // cp.async fill, cooperative: block b may be written once every warp has released bucket b - nblk.
@@ -608,6 +624,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   DBG_T0(tc);
   auto observe = [&](int upto) {
     DBG_T0(t1);
+    // the single producer arrives block after block, so block b landed implies all earlier ones; a
+    // parity test is valid as long as the block one phase earlier (b - nblk) is known to have landed
+    if (FILL && upto > landed && upto - 1 - nblk < landed) landed = upto - 1;
     for (; landed < upto; ++landed) wait_on(&full_bar[landed % nblk], (uint32_t)((landed / nblk) & 1));
     DBG_ACC(1, t1);
   };
@@ -617,6 +636,19 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   // ahead), and before arriving for bucket j it waits for the phase of bucket j - nblk (a warp that
   // skips far ahead on a sparse frame would otherwise be counted twice in that older phase).
   auto release = [&](int to) {
+    if (FILL) {
+      // TMA fill: publish the bucket this warp now works in; the producer polls the minimum.  All
+      // taps of earlier items have been consumed by the time this store issues.
+      if (to > cur) {
+        cur = to;
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          *reinterpret_cast<volatile int*>(&s_progress[warp]) = to;
+        }
+      }
+      return;
+    }
     for (int j = cur; j < to; ++j) {
       observe(j + 1);
       {
@@ -641,9 +673,12 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int nxt = claim();
     if (nxt < n_items) rec_next = __ldg(recs + (size_t)nxt * kRecVec + lane);
     const float4 hdr = slot[0];
-    const int r = __float_as_int(hdr.x), code = __float_as_int(hdr.y), bucket = __float_as_int(hdr.z);
+    // header fields are warp-uniform; the reductions make that visible to ptxas (uniform branches / loops)
+    const int r = __float_as_int(hdr.x);
+    const int code = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.y));
+    const int bucket = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
-    float* o = a.out + ((size_t)r * C + c0) * bins + ph0 * kP;
+    float* o = out_g + ((size_t)r * C + c0) * bins + ph0 * kP;
     if (!(code >> 16)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       release(bucket);
@@ -665,7 +700,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     } else {
       // bin-row taller than the resident window: taps straight from global memory (rare)
       const bool ch_ok = lane < nch;
-      const float* roi = a.L.rois + (size_t)r * 5;
+      const float* roi = rois_g + (size_t)r * 5;
       const float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
       const RoiGeom g = roi_geometry(rr, a.ws.scale, kP, kP, S, a.ws.aligned != 0);
       const float* plane = fbase + (size_t)(ch_ok ? lane : 0) * H * W;
@@ -778,7 +813,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
                                                           p.nsteps, p.row_words * 4, items_cap, ws);              \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
-    fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap);                                                  \
+    fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap, feat, ws.records, L.rois, out);                    \
     B2D_LAUNCHED();                                                                                               \
   } while (0)
 #define B2D_ROWS_S(FF)           \
