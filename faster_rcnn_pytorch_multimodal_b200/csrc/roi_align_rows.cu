@@ -451,7 +451,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const int row_words = a.row_words;
   const float* fbase = feat_g + ((size_t)f * C + c0) * H * W;
   // dynamic shared: [ring (128-byte aligned)][record slots][staging tiles]
-  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);
+  // (pointer arithmetic on `smem` keeps the shared address space; a cast through an integer would
+  // turn every slot / staging access into a generic load)
+  float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
   float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * 2 * kCh * kP;
   float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * 2 * kCh * kP;
@@ -664,14 +666,16 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   pump();
   int pending = claim();
   float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (pending < n_items) rec_next = __ldg(recs + (size_t)pending * kRecVec + lane);
+  // (record loads are unconditional - clamped index - so that the prefetch is not followed by a
+  // select that would wait for it)
+  rec_next = __ldg(recs + (size_t)min(pending, max(n_items - 1, 0)) * kRecVec + lane);
 
   while (pending < n_items) {
     pump();
     slot[lane] = rec_next;
     __syncwarp();
     const int nxt = claim();
-    if (nxt < n_items) rec_next = __ldg(recs + (size_t)nxt * kRecVec + lane);
+    rec_next = __ldg(recs + (size_t)min(nxt, n_items - 1) * kRecVec + lane);
     const float4 hdr = slot[0];
     // header fields are warp-uniform; the reductions make that visible to ptxas (uniform branches / loops)
     const int r = __float_as_int(hdr.x);
