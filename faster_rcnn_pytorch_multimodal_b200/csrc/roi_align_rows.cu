@@ -58,6 +58,18 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #define DBG_ACC(slot, v)
 #endif
 
+#ifndef B2D_STAGES
+#define B2D_STAGES 2
+#endif
+#ifndef B2D_OUT_TILES
+#define B2D_OUT_TILES 2
+#endif
+#ifndef B2D_EARLY
+#define B2D_EARLY 0
+#endif
+#ifndef B2D_SLACK
+#define B2D_SLACK 2
+#endif
 constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
@@ -69,7 +81,8 @@ constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 
-constexpr int kStages = 2;         // staging rows of the TMA fill
+constexpr int kStages = B2D_STAGES;         // staging rows of the TMA fill
+constexpr int kProducers = 2;      // producer warps of the TMA fill (each repacks 32 / kProducers channels)
 
 struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
@@ -88,7 +101,7 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   p.row_words = kCh * pitch;
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * W * 4 : 0;
-  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * 2 * kCh * kP * 4 + 256 + staging;
+  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging;
   const size_t budget = 227 * 1024 - 2048;
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
@@ -99,7 +112,7 @@ static Plan make_plan(int H, int W, bool allow_tma) {
     if (St < 1) St = 1;
     Rr -= Rr % St;                                   // blocks of St rows never wrap inside the ring
     const int nblk = Rr / St;
-    const int slack = nblk >= 12 ? 3 : (nblk >= 8 ? 2 : 1);
+    const int slack = nblk >= 12 ? 3 : (nblk >= 8 ? B2D_SLACK : 1);
     p.Rr = Rr; p.St = St; p.nblk = nblk; p.nbk = nblk - slack;
     p.span_max = (p.nbk - 1) * St + 1;
     p.nsteps = ceil_div(H, St);
@@ -334,10 +347,10 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 }
 
 // One item: nph = NPH bin-rows of one RoI for this lane's channel.
-template <int NPH, int S>
+template <int NPH, int S, class AfterRows>
 __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
-                                         const int (&ooff)[kP], unsigned omask) {
+                                         const int (&ooff)[kP], unsigned omask, AfterRows after_rows) {
   constexpr int NX = kP * S;
   constexpr int RV = NPH > 3 ? 2 : 1;
   uint32_t xa[NX];
@@ -403,11 +416,13 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       for (int p = 0; p < NPH; ++p) acc[p][pw] = fmaf(wy[p], t, acc[p][pw]);
     }
   }
+  after_rows();      // the ring is not needed any more: lets the caller release it early
   // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw); two
   // tiles alternate, so the shared-memory round trip of bin-row p overlaps the staging of p + 1
 #pragma unroll
   for (int p = 0; p < NPH; ++p) {
-    float* tile = stage + (p & 1) * (kCh * kP);
+    float* tile = stage + (B2D_OUT_TILES > 1 ? (p & 1) * (kCh * kP) : 0);
+    if (B2D_OUT_TILES == 1 && p > 0) __syncwarp();
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) tile[lane * kP + pw] = acc[p][pw];
     __syncwarp();
@@ -438,7 +453,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   __shared__ __align__(8) uint64_t stg_bar[kStages];    // staging row landed (TMA bytes)
   __shared__ int s_ctr;
   __shared__ int s_progress[kWarps];                    // TMA fill: bucket each consumer warp is working in
-  constexpr int kConsumers = FILL ? kWarps - 1 : kWarps;
+  constexpr int kConsumers = FILL ? kWarps - kProducers : kWarps;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * kCh;
@@ -455,15 +470,15 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   // turn every slot / staging access into a generic load)
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
-  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * 2 * kCh * kP;
-  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * 2 * kCh * kP;
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * B2D_OUT_TILES * kCh * kP;
+  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * B2D_OUT_TILES * kCh * kP;
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
   if (tid == 0) {
     s_ctr = 0;
     for (int i = 0; i < kStages; ++i) mbar_init(&stg_bar[i], 1);
     for (int i = 0; i < nblk; ++i) {
-      mbar_init(&full_bar[i], FILL ? 1 : kThreads);
+      mbar_init(&full_bar[i], FILL ? kProducers : kThreads);
       mbar_init(&done_bar[i], kConsumers);
     }
   }
@@ -477,7 +492,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   }
   __syncthreads();
 
-  if (FILL && warp == kWarps - 1) {
+  if (FILL && warp >= kConsumers) {
     // ---------------- producer: one tiled TMA per feature row (box = [32 planes][W]) into a dense
     // staging buffer, then repack the staged row into its skewed ring slot
 #ifdef B2D_ROWS_TIMING
@@ -488,8 +503,10 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int nchunk = (W + 31) / 32;
     const bool tail_ok = lane + 32 * (nchunk - 1) < W;
     const int plane0 = f * C + c0;
+    const int pw_id = warp - kConsumers;                    // which producer
+    constexpr int kChP = kCh / kProducers;                  // channels this producer repacks
     auto fetch = [&](int y) {        // row y of the 32 channels -> staging buffer y % kStages
-      if (lane == 0) {
+      if (pw_id == 0 && lane == 0) {
         uint64_t* bar = &stg_bar[y % kStages];
         mbar_expect_tx(bar, row_tx);
         tma_load_2d(smem_u32(stg + (size_t)(y % kStages) * kCh * W), &tmap, y * W, plane0, bar);
@@ -516,11 +533,12 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
         mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
         DBG_ACC(6, t2);
       }
-      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * W) + (uint32_t)lane * 4u;
-      uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u;
       const uint32_t sstep = (uint32_t)W * 4u, dstep = (uint32_t)a.lane_stride * 4u;
+      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * W) + (uint32_t)lane * 4u + (uint32_t)(pw_id * kChP) * sstep;
+      uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
+                     (uint32_t)(pw_id * kChP) * dstep;
       // 8 channels x up to 4 chunks (32 values) in flight per lane
-      for (int c8 = 0; c8 < nch; c8 += 8) {
+      for (int c8 = 0; c8 < kChP; c8 += 8) {
         for (int cg = 0; cg < nchunk; cg += 4) {
           float v[32];
 #pragma unroll
@@ -544,6 +562,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
         dst += 8 * dstep;
       }
       __syncwarp();
+      if (kProducers > 1) asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");   // all producers done with the buffer
       {
         DBG_T0(t4);
         if (y + kStages < H) fetch(y + kStages);     // this staging buffer is free again
@@ -687,15 +706,23 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       release(bucket);
       observe(min(bucket + nbk, nsteps));
+      // once the rows of this item are done the warp only needs what its NEXT item needs (already
+      // claimed, record in flight since the top of the loop): publish that bucket before the output
+      // phase so the producer can refill while this warp stages and stores
+      auto early = [&]() {
+        if (!FILL || !B2D_EARLY) return;
+        const unsigned nb_next = __reduce_max_sync(0xffffffffu, lane == 0 ? (unsigned)__float_as_int(rec_next.z) : 0u);
+        release(nxt < n_items ? (int)nb_next : nsteps);
+      };
       DBG_T0(t3);
       switch (nph) {
-        case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        case 3: run_item<3, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        case 4: run_item<4, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        case 5: run_item<5, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
-        default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask); break;
+        case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        case 3: run_item<3, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        case 4: run_item<4, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        case 5: run_item<5, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+        default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
       }
       DBG_ACC(3, t3);
 #ifdef B2D_ROWS_TIMING
