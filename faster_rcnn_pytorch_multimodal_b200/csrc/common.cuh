@@ -9,7 +9,9 @@ namespace b2d {
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 constexpr int kMaxSortElems = 16384;  // in-CTA bitonic capacity (128 KB of u64 keys)
-constexpr int kSelectBins = 65536;    // 16-bit first-level radix histogram
+constexpr int kSelectBits = 14;       // first-level radix: top bits of the score key (64 KB shared histogram per CTA)
+constexpr int kSelectBins = 1 << kSelectBits;
+constexpr int kSelectShift = 32 - kSelectBits;
 
 extern std::atomic<uint64_t> g_launches;
 extern thread_local int tl_cuda_error;

@@ -59,10 +59,10 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #endif
 
 #ifndef B2D_STAGES
-#define B2D_STAGES 2
+#define B2D_STAGES 3
 #endif
 #ifndef B2D_OUT_TILES
-#define B2D_OUT_TILES 2
+#define B2D_OUT_TILES 1
 #endif
 #ifndef B2D_EARLY
 #define B2D_EARLY 0
