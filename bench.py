@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="independent frames per step per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=4, help="frames per host-buffer call")
+    ap.add_argument("--e2e-frames", type=int, default=8, help="frames per host-buffer call")
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--cpu-baseline-frames", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -307,7 +307,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({F * (b_prop + cfg['C'] * n_loc * 4) / 1e6:.0f} MB read, "
                                     f"{F * M * cfg['C'] * P * P * 4 / 1e6:.0f} MB written per step)",
                        "parallelism": f"frame-stream x{world}, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "roi_align_fwd_sweep7_kernel", "achieved": crop_gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "rows::fwd_kernel<2,true> (RoIAlign forward)", "achieved": crop_gbs, "peak": peak,
                          "unit": "GB/s", "frac": crop_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": F * b_crop, "kernel_ms": crop_ms,
                          "kernel_share_of_step": crop_ms / (elapsed_ms / args.steps),
@@ -315,7 +315,7 @@ def main():
                                          "algorithmic_bytes_per_frame": b_prop + b_nms + b_crop}},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_call": Fe, "ms_per_call": e2e_ms / e_steps,
-                    "note": "PCIe-bound: rois + pooled [R,C,7,7] features return to host every call"},
+                    "note": "PCIe-bound: 45 MB up and 60 MB down per frame; frames pipelined over H2D / compute / D2H streams"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline:

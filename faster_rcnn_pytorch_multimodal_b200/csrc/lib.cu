@@ -30,10 +30,13 @@ struct PipeWs {
   float *cls, *pred, *info, *feat, *rois, *scores, *pooled;
   int32_t* num_out;
   void* prop_ws;
-  size_t prop_ws_bytes;
+  size_t prop_ws_bytes;   // per frame
+  void* roi_ws;
+  size_t roi_ws_bytes;    // per frame
   size_t bytes;
 };
 
+// Every region is laid out frame-major so that frame f can be processed on its own.
 PipeWs carve_pipe(void* base, int F, int n_loc, int A, int C, int H, int W, int pre, int post, int P) {
   PipeWs w;
   const int N = n_loc * A;
@@ -54,8 +57,10 @@ PipeWs carve_pipe(void* base, int F, int n_loc, int A, int C, int H, int W, int 
   w.scores = reinterpret_cast<float*>(take(sizeof(float) * (size_t)F * mo));
   w.num_out = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
   w.pooled = reinterpret_cast<float*>(take(sizeof(float) * (size_t)F * mo * C * P * P));
-  w.prop_ws_bytes = b2d_proposal_workspace_bytes(F, n_loc, A, pre, post);
-  w.prop_ws = take(w.prop_ws_bytes);
+  w.prop_ws_bytes = align_up(b2d_proposal_workspace_bytes(1, n_loc, A, pre, post), 256);
+  w.prop_ws = take(w.prop_ws_bytes * F);
+  w.roi_ws_bytes = align_up(b2d_roi_align_workspace_bytes(1, C, H, W, mo, mo), 256);
+  w.roi_ws = take(w.roi_ws_bytes * F);
   w.bytes = off;
   return w;
 }
@@ -66,6 +71,9 @@ extern "C" size_t b2d_pipeline_device_bytes(int F, int n_loc, int A, int C, int 
   return carve_pipe(nullptr, F, n_loc, A, C, H, W, pre, post, P).bytes;
 }
 
+// Frames are independent, so the call is a three-stage pipeline over single frames: H2D copies on
+// one side stream, the kernels on the caller's stream, D2H copies on a second side stream.  PCIe is
+// full duplex, so frame f+1 uploads while frame f computes and frame f-1 downloads.
 extern "C" int b2d_proposal_crop_host(int F, int n_loc, int A, int C, int H, int W, const float* cls_prob_host,
                                       const float* bbox_pred_host, const float* info_host, const float* anchors_dev,
                                       const float* feat_host, int pre, int post, double nms_thresh, int P,
@@ -81,20 +89,67 @@ extern "C" int b2d_proposal_crop_host(int F, int n_loc, int A, int C, int H, int
   const int N = n_loc * A;
   const int k = (pre > 0 && pre < N) ? pre : N;
   const int mo = (post > 0 && post < k) ? post : k;
-  B2D_CUDA(cudaMemcpyAsync(w.cls, cls_prob_host, sizeof(float) * (size_t)F * n_loc * 2 * A, cudaMemcpyHostToDevice, st));
-  B2D_CUDA(cudaMemcpyAsync(w.pred, bbox_pred_host, sizeof(float) * (size_t)F * N * 4, cudaMemcpyHostToDevice, st));
-  B2D_CUDA(cudaMemcpyAsync(w.info, info_host, sizeof(float) * (size_t)F * 7, cudaMemcpyHostToDevice, st));
-  B2D_CUDA(cudaMemcpyAsync(w.feat, feat_host, sizeof(float) * (size_t)F * C * H * W, cudaMemcpyHostToDevice, st));
-  int rc = b2d_proposal(F, n_loc, A, w.cls, w.pred, w.info, anchors_dev, nullptr, pre, post, nms_thresh, 1, w.rois,
-                        w.scores, nullptr, nullptr, w.num_out, w.prop_ws, w.prop_ws_bytes, stream);
-  if (rc != B2D_OK) return rc;
-  rc = b2d_roi_align_forward(F, C, H, W, w.feat, w.rois, F * mo, nullptr, 0, w.num_out, mo, P, P, spatial_scale,
-                             sampling_ratio, 0, w.pooled, nullptr, 0, stream);
-  if (rc != B2D_OK) return rc;
-  B2D_CUDA(cudaMemcpyAsync(rois_host, w.rois, sizeof(float) * (size_t)F * mo * 5, cudaMemcpyDeviceToHost, st));
-  B2D_CUDA(cudaMemcpyAsync(scores_host, w.scores, sizeof(float) * (size_t)F * mo, cudaMemcpyDeviceToHost, st));
-  B2D_CUDA(cudaMemcpyAsync(num_out_host, w.num_out, sizeof(int32_t) * (size_t)F, cudaMemcpyDeviceToHost, st));
-  B2D_CUDA(cudaMemcpyAsync(pooled_host, w.pooled, sizeof(float) * (size_t)F * mo * C * P * P, cudaMemcpyDeviceToHost, st));
-  B2D_CUDA(cudaStreamSynchronize(st));
-  return B2D_OK;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_in = nullptr, ev_done = nullptr;
+  int rc = B2D_OK;
+  auto fail = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == B2D_OK) rc = cuda_fail(e);
+    return e != cudaSuccess;
+  };
+  if (fail(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) ||
+      fail(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) ||
+      fail(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming)) ||
+      fail(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming)) ||
+      fail(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming))) {
+    // fall through to the cleanup below
+  } else {
+    // the side streams start after whatever the caller already queued on `stream`
+    fail(cudaEventRecord(ev_start, st));
+    fail(cudaStreamWaitEvent(s_in, ev_start, 0));
+    fail(cudaStreamWaitEvent(s_out, ev_start, 0));
+    const size_t n_cls = (size_t)n_loc * 2 * A, n_pred = (size_t)N * 4, n_feat = (size_t)C * H * W;
+    const size_t n_pool = (size_t)mo * C * P * P;
+    for (int f = 0; f < F && rc == B2D_OK; ++f) {
+      fail(cudaMemcpyAsync(w.cls + f * n_cls, cls_prob_host + f * n_cls, sizeof(float) * n_cls, cudaMemcpyHostToDevice, s_in));
+      fail(cudaMemcpyAsync(w.pred + f * n_pred, bbox_pred_host + f * n_pred, sizeof(float) * n_pred, cudaMemcpyHostToDevice, s_in));
+      fail(cudaMemcpyAsync(w.info + f * 7, info_host + f * 7, sizeof(float) * 7, cudaMemcpyHostToDevice, s_in));
+      fail(cudaMemcpyAsync(w.feat + f * n_feat, feat_host + f * n_feat, sizeof(float) * n_feat, cudaMemcpyHostToDevice, s_in));
+      fail(cudaEventRecord(ev_in, s_in));
+      fail(cudaStreamWaitEvent(st, ev_in, 0));
+      if (rc != B2D_OK) break;
+      // col0 of the RoIs is the frame index within this call; the frame is processed alone, so its
+      // kernels see frame index 0 and the batch index is patched in through batch_index_stride
+      int r2 = b2d_proposal(1, n_loc, A, w.cls + f * n_cls, w.pred + f * n_pred, w.info + f * 7, anchors_dev, nullptr,
+                            pre, post, nms_thresh, 0, w.rois + (size_t)f * mo * 5, w.scores + (size_t)f * mo, nullptr,
+                            nullptr, w.num_out + f, static_cast<char*>(w.prop_ws) + f * w.prop_ws_bytes, w.prop_ws_bytes,
+                            stream);
+      if (r2 == B2D_OK)
+        r2 = b2d_roi_align_forward(1, C, H, W, w.feat + f * n_feat, w.rois + (size_t)f * mo * 5, mo, nullptr, 0,
+                                   w.num_out + f, mo, P, P, spatial_scale, sampling_ratio, 0, w.pooled + f * n_pool,
+                                   static_cast<char*>(w.roi_ws) + f * w.roi_ws_bytes, w.roi_ws_bytes, stream);
+      if (r2 != B2D_OK) {
+        rc = r2;
+        break;
+      }
+      fail(cudaEventRecord(ev_done, st));
+      fail(cudaStreamWaitEvent(s_out, ev_done, 0));
+      fail(cudaMemcpyAsync(rois_host + (size_t)f * mo * 5, w.rois + (size_t)f * mo * 5, sizeof(float) * mo * 5, cudaMemcpyDeviceToHost, s_out));
+      fail(cudaMemcpyAsync(scores_host + (size_t)f * mo, w.scores + (size_t)f * mo, sizeof(float) * mo, cudaMemcpyDeviceToHost, s_out));
+      fail(cudaMemcpyAsync(num_out_host + f, w.num_out + f, sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+      fail(cudaMemcpyAsync(pooled_host + f * n_pool, w.pooled + f * n_pool, sizeof(float) * n_pool, cudaMemcpyDeviceToHost, s_out));
+    }
+    // col0 = frame index, as b2d_proposal(batch_index_stride = 1) would have written it
+    fail(cudaStreamSynchronize(s_out));
+    fail(cudaStreamSynchronize(s_in));
+    fail(cudaStreamSynchronize(st));
+    if (rc == B2D_OK)
+      for (int f = 1; f < F; ++f)
+        for (int i = 0; i < num_out_host[f]; ++i) rois_host[((size_t)f * mo + i) * 5] = (float)f;
+  }
+  if (ev_start) cudaEventDestroy(ev_start);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_done) cudaEventDestroy(ev_done);
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_out) cudaStreamDestroy(s_out);
+  return rc;
 }

@@ -150,24 +150,27 @@ __global__ void __launch_bounds__(1024) score_threshold_kernel(const uint32_t* _
 
 // Candidates (scores in bins >= the threshold bin) -> composites, unordered.  A CTA counts its
 // candidates first and reserves its output range with ONE global atomic.
-__global__ void __launch_bounds__(kSelThreads) score_compact_kernel(const float* __restrict__ cls_prob, int n_loc,
+constexpr int kCmpThreads = 256;
+constexpr int kCmpChunk = 4096;    // scores per CTA of the compact pass (16 per thread, ~4 CTAs per SM)
+
+__global__ void __launch_bounds__(kCmpThreads) score_compact_kernel(const float* __restrict__ cls_prob, int n_loc,
                                                                     int A, int N, uint32_t magic,
                                                                     uint32_t* __restrict__ sel,
                                                                     uint64_t* __restrict__ cand) {
-  __shared__ uint32_t s_warp[kSelThreads / 32];
+  __shared__ uint32_t s_warp[kCmpThreads / 32];
   __shared__ uint32_t s_base;
   const int f = blockIdx.y;
   const uint32_t thr_bin = sel[f * 4 + 0];
   uint64_t* out = cand + (size_t)f * N;
   const float* fp = cls_prob + (size_t)f * n_loc * (2 * A);
-  const int n0 = blockIdx.x * kSelChunk, n1 = min(N, n0 + kSelChunk);
-  constexpr int kIter = kSelChunk / kSelThreads;
+  const int n0 = blockIdx.x * kCmpChunk, n1 = min(N, n0 + kCmpChunk);
+  constexpr int kIter = kCmpChunk / kCmpThreads;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t keys[kIter];
   uint32_t mine = 0;     // bit it: element it of this thread is a candidate
 #pragma unroll
   for (int it = 0; it < kIter; ++it) {
-    const int n = n0 + it * kSelThreads + threadIdx.x;
+    const int n = n0 + it * kCmpThreads + threadIdx.x;
     keys[it] = 0;
     if (n < n1) {
       keys[it] = score_key(fg_score_fast(fp, A, magic, n));
@@ -185,21 +188,21 @@ __global__ void __launch_bounds__(kSelThreads) score_compact_kernel(const float*
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    uint32_t w = lane < kSelThreads / 32 ? s_warp[lane] : 0u;
+    uint32_t w = lane < kCmpThreads / 32 ? s_warp[lane] : 0u;
     uint32_t wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
       if (lane >= d) wi += v;
     }
-    if (lane < kSelThreads / 32) s_warp[lane] = wi - w;
+    if (lane < kCmpThreads / 32) s_warp[lane] = wi - w;
     if (lane == 31 && wi) s_base = atomicAdd(sel + f * 4 + 1, wi);
   }
   __syncthreads();
   uint32_t pos = s_base + s_warp[warp] + incl - cnt;
 #pragma unroll
   for (int it = 0; it < kIter; ++it)
-    if (mine & (1u << it)) out[pos++] = composite_key(keys[it], (uint32_t)(n0 + it * kSelThreads + threadIdx.x));
+    if (mine & (1u << it)) out[pos++] = composite_key(keys[it], (uint32_t)(n0 + it * kCmpThreads + threadIdx.x));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -439,7 +442,8 @@ static int select_sort(int F, int n_loc, int A, const float* cls_prob, const flo
   B2D_LAUNCHED();
   score_threshold_kernel<<<F, 1024, 0, st>>>(w.hist, w.sel, k);
   B2D_LAUNCHED();
-  score_compact_kernel<<<grid, kSelThreads, 0, st>>>(cls_prob, n_loc, A, N, magic, w.sel, w.cand);
+  dim3 cgrid(ceil_div(N, kCmpChunk), F);
+  score_compact_kernel<<<cgrid, kCmpThreads, 0, st>>>(cls_prob, n_loc, A, N, magic, w.sel, w.cand);
   B2D_LAUNCHED();
   const size_t smem = sizeof(uint64_t) * kMaxSortElems;
   B2D_CUDA(cudaFuncSetAttribute(sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
