@@ -70,7 +70,10 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #ifndef B2D_SLACK
 #define B2D_SLACK 2
 #endif
-constexpr int kWarps = 12;
+#ifndef B2D_WARPS
+#define B2D_WARPS 10
+#endif
+constexpr int kWarps = B2D_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
 constexpr int kP = 7;              // PH = PW = 7
