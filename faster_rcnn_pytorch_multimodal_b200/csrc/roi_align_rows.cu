@@ -819,7 +819,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
                            cudaStream_t st) {
   using namespace rows;
   if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 27)) return B2D_ERR_UNSUPPORTED;
-  static const bool coop = getenv("B2D_ROWS_COOP_FILL") != nullptr;   // debugging knob: force the cp.async fill
+  const bool coop = getenv("B2D_ROWS_COOP_FILL") != nullptr;   // test knob: force the cp.async fill
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   const Plan p = make_plan(H, W, !coop && make_tmap(&tmap, feat, F, C, H, W));

@@ -363,6 +363,79 @@ def test_roi_align_forward_backward_vs_torchvision(C, H, W, R, sr):
     close(f_gpu.grad, f_ref.grad, atol=1e-5 * float(f_ref.grad.abs().max()))
 
 
+def _stress_rois(seed, F, M, W, H):
+    """Proposal-like mix incl. the awkward cases: tiny, full-frame (taller than the ring window),
+    zero-area, partly and wholly outside the frame."""
+    g = torch.Generator().manual_seed(seed)
+    r = _random_rois(seed, F * M, W, H, F=F).view(F, M, 5)
+    for f in range(F):
+        r[f, :, 0] = f
+        r[f, 0, 1:] = torch.tensor([0.0, 0.0, W - 1.0, H - 1.0])                # whole frame
+        r[f, 1, 1:] = torch.tensor([W * 0.4, 0.0, W * 0.45, H - 1.0])           # tall and thin
+        r[f, 2, 1:] = torch.tensor([100.0, 100.0, 100.0, 100.0])                # zero area
+        r[f, 3, 1:] = torch.tensor([-300.0, -300.0, -200.0, -150.0])            # outside (top-left)
+        r[f, 4, 1:] = torch.tensor([W + 50.0, H + 40.0, W + 400.0, H + 300.0])  # outside (bottom-right)
+        r[f, 5, 1:] = torch.tensor([W - 40.0, H - 30.0, W + 200.0, H + 100.0])  # straddles the corner
+        r[f, 6, 1:] = torch.tensor([33.3, 47.1, 36.2, 49.9])                    # sub-pixel
+    return r.view(-1, 5)
+
+
+@pytest.mark.parametrize("coop", [False, True])
+@pytest.mark.parametrize("sr", [2, 1])
+def test_roi_align_rows_kernel_waymo_shape(coop, sr, monkeypatch):
+    """The streaming 'rows' kernel at the BASELINE feature-map size (80x120 ring, TMA and cp.async fills)."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    if coop:
+        monkeypatch.setenv("B2D_ROWS_COOP_FILL", "1")
+    F, C, H, W, M = 2, 64, 80, 120, 300
+    g = torch.Generator().manual_seed(11)
+    feat = torch.randn(F, C, H, W, generator=g)
+    rois = _stress_rois(5, F, M, W * 16, H * 16)
+    cnt = torch.tensor([M, M - 7], dtype=torch.int32)
+    got = ops.roi_align(feat.to(dev()), rois.to(dev()), (7, 7), 1.0 / 16, sr, False, seg_count=cnt.to(dev()), seg_stride=M)
+    want = O.roi_align(feat, rois, (7, 7), 1.0 / 16, sr, False).view(F, M, C, 7, 7)
+    want[1, M - 7:] = 0
+    close(got.view(F, M, C, 7, 7), want, atol=1e-5)
+
+
+def test_roi_align_rows_kernel_sparse_and_dense_frames():
+    """3 RoIs on a tall map (warps skip many buckets) and 2000 RoIs (TRAIN post-NMS count)."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(1, 32, 80, 120, generator=g)
+    for R in (3, 2000):
+        rois = _random_rois(R, R, 120 * 16, 80 * 16)
+        got = ops.roi_align(feat.to(dev()), rois.to(dev()), (7, 7), 1.0 / 16, 2, False)
+        close(got, O.roi_align(feat, rois, (7, 7), 1.0 / 16, 2, False), atol=1e-5)
+    empty = ops.roi_align(feat.to(dev()), torch.zeros(0, 5, device=dev()), (7, 7), 1.0 / 16, 2, False)
+    assert tuple(empty.shape) == (0, 32, 7, 7)
+
+
+def test_roi_align_full_size_properties():
+    """Size-independent properties at BASELINE config[1] size (C=1024, 80x120, 300 RoIs): bilinear
+    weights of in-frame samples sum to one, and the op is linear in the feature map."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    C, H, W, R = 1024, 80, 120, 300
+    g = torch.Generator(device=dev()).manual_seed(4)
+    rois = _random_rois(21, R, W * 16 - 700, H * 16 - 700).to(dev())
+    rois[:, 1:] = rois[:, 1:].clamp(min=0)
+    rois[:, 3] = rois[:, 3].clamp(max=W * 16 - 17)
+    rois[:, 4] = rois[:, 4].clamp(max=H * 16 - 17)
+    ones = ops.roi_align(torch.full((1, C, H, W), 2.5, device=dev()), rois, (7, 7), 1.0 / 16, 2, False)
+    close(ones, torch.full_like(ones, 2.5).cpu(), atol=1e-5)
+    f1 = torch.randn(1, C, H, W, generator=g, device=dev())
+    f2 = torch.randn(1, C, H, W, generator=g, device=dev())
+    a = ops.roi_align(f1, rois, (7, 7), 1.0 / 16, 2, False)
+    b = ops.roi_align(f2, rois, (7, 7), 1.0 / 16, 2, False)
+    ab = ops.roi_align(0.5 * f1 - 2.0 * f2, rois, (7, 7), 1.0 / 16, 2, False)
+    close(ab, (0.5 * a - 2.0 * b).cpu(), atol=2e-5)
+    # channel c of the output depends on channel c of the input only
+    f3 = f1.clone()
+    f3[:, 512:] = 0
+    c = ops.roi_align(f3, rois, (7, 7), 1.0 / 16, 2, False)
+    assert torch.equal(c[:, :512], a[:, :512]) and float(c[:, 512:].abs().max()) == 0.0
+
+
 def test_roi_align_multi_frame_and_padded_segments():
     from faster_rcnn_pytorch_multimodal_b200 import ops
     F, C, H, W, M = 3, 24, 24, 78, 50
