@@ -1,3 +1,5 @@
+"""Cycle breakdown of rows::fwd_kernel (consumer waits / run_item / producer): build the library with -DB2D_ROWS_TIMING first
+(see csrc/roi_align_rows.cu), then run this on a GPU box."""
 import ctypes, sys, subprocess, os, json
 sys.path.insert(0, '/root/repo')
 import torch, bench
