@@ -236,3 +236,48 @@ def fpn_level_map(boxes: torch.Tensor, k_min: int, k_max: int, canonical_scale: 
                                   int(canonical_level), float(eps), ptr(out), stream_ptr(boxes.device)),
           "b2d_fpn_level_map")
     return out.long()
+
+
+# ------------------------------------------------------------------------------------------
+# Final per-class detection filter (utils/filter_predictions.py:45-130, model/test.py:213-221)
+# ------------------------------------------------------------------------------------------
+def final_detections(cls_score, pred_boxes, info, num_elem, db_type, score_thresh, nms_thresh, max_dets=0,
+                     num_rois=None, uc_row=None, uc_cls=None, max_out=None):
+    """Batched on-device replacement of the per-class threshold + NMS + gather loop.
+
+    cls_score [F,R,K], pred_boxes [F,R,K*E] (decoded), info [F,7]; db_type 'image' (boxes clamped to the
+    frame) | 'lidar' | 'image_noclamp'.
+    uc_row [F,R,U] per-roi and uc_cls [F,R,U2,K*E] per-class-box uncertainty columns are optional.
+    -> dets [F,K,max_out,E+1] (box, score; descending score; zero padded), det_roi [F,K,max_out] int32
+       (source roi, -1 padded), counts [F,K] int32, out_uc_row [F,K,max_out,U] | None,
+       out_uc_cls [F,K,max_out,U2*E] | None.  One launch, no host sync.
+    """
+    require_cuda(cls_score, pred_boxes, info, num_rois, uc_row, uc_cls)
+    modes = {"image": 0, "lidar": 1, "image_noclamp": 2}
+    if db_type not in modes:
+        raise _lib.B2DError(f"final_detections: db_type must be one of {sorted(modes)}, got {db_type!r}")
+    sc, pb, inf = f32c(cls_score), f32c(pred_boxes), f32c(info)
+    F, R, K = sc.shape
+    E = int(num_elem)
+    if pb.shape != (F, R, K * E) or inf.shape != (F, 7):
+        raise _lib.B2DError("final_detections: shape mismatch")
+    mo = int(max_out) if max_out else max(R, 1)
+    dev = sc.device
+    dets = torch.empty(F, K, mo, E + 1, device=dev)
+    det_roi = torch.empty(F, K, mo, dtype=torch.int32, device=dev)
+    counts = torch.empty(F, K, dtype=torch.int32, device=dev)
+    if K > 0:
+        dets[:, 0].zero_()
+        det_roi[:, 0].fill_(-1)
+    ur = f32c(uc_row) if uc_row is not None else None
+    ucl = f32c(uc_cls) if uc_cls is not None else None
+    n_ur = ur.shape[2] if ur is not None else 0
+    n_uc = ucl.shape[2] if ucl is not None else 0
+    o_ur = torch.zeros(F, K, mo, n_ur, device=dev) if n_ur else None
+    o_uc = torch.zeros(F, K, mo, n_uc * E, device=dev) if n_uc else None
+    nr = num_rois.to(torch.int32).contiguous() if num_rois is not None else None
+    check(lib().b2d_final_detections(F, R, K, E, ptr(sc), ptr(pb), ptr(nr), ptr(inf), modes[db_type],
+                                     float(score_thresh), float(nms_thresh), int(max_dets), mo, ptr(ur), n_ur,
+                                     ptr(ucl), n_uc, ptr(dets), ptr(det_roi), ptr(o_ur), ptr(o_uc), ptr(counts),
+                                     stream_ptr(dev)), "b2d_final_detections")
+    return dets, det_roi, counts, o_ur, o_uc

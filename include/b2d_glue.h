@@ -236,6 +236,30 @@ int b2d_mc_class_uncertainty(int num_samples, int n, int num_classes, const floa
 int b2d_var_sort(int n, int cols, const float* var, int descending, float* key, int32_t* order, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Final per-class detection filter, batched over frames and classes.
+ * Replaces nms_hstack_torch() / filter_and_draw_prep()  utils/filter_predictions.py:45-130
+ *          and the max-dets filter of the test loop       model/test.py:213-221.
+ *   cls_score [F,R,K]; pred_boxes [F,R,K*E] (already decoded); num_rois [F] or NULL; info [F,7].
+ *   lidar = 0: boxes clamped to [0, w/scale-1] x [0, h/scale-1] (:82-91), NMS on the box;
+ *   lidar = 1: NMS on the un-rotated AABB of (xc, yc, l, w) = elements 0,1,3,4 (:58-62);
+ *   lidar = 2: image boxes taken as they are (nms_hstack_torch() called on its own, :45-72).
+ *   Per class c >= 1: rois with score > score_thresh, descending score (ties: lower roi first),
+ *   greedy NMS (torchvision semantics, (double)iou > nms_thresh), then max_dets (> 0): keep
+ *   scores >= the max_dets-th best (ties kept).
+ *   uc_row [F,R,n_uc_row] per-roi uncertainty columns (entropy, mutual information, ...) and
+ *   uc_cls [F,R,n_uc_cls,K*E] per-class-box columns (bbox variances) are gathered alongside.
+ * Outputs, padded to max_out rows per (frame, class) with zeros / -1:
+ *   dets [F,K,max_out,E+1] = box, score; det_roi [F,K,max_out] source roi; counts [F,K];
+ *   out_uc_row [F,K,max_out,n_uc_row]; out_uc_cls [F,K,max_out,n_uc_cls*E].  R <= 1024.
+ * ---------------------------------------------------------------------------------- */
+int b2d_final_detections(int num_frames, int num_rois_max, int num_classes, int num_elem,
+                         const float* cls_score, const float* pred_boxes, const int32_t* num_rois,
+                         const float* info, int lidar, float score_thresh, double nms_thresh, int max_dets,
+                         int max_out, const float* uc_row, int n_uc_row, const float* uc_cls, int n_uc_cls,
+                         float* dets, int32_t* det_roi, float* out_uc_row, float* out_uc_cls, int32_t* counts,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------
  * End-to-end entry with HOST buffers (bench.py `e2e`): H2D of a frame batch, proposal
  * stage, RoIAlign forward, D2H of rois / scores / counts / pooled features.  Host buffers
  * should be pinned.  device_ws must hold b2d_pipeline_device_bytes().  Blocks until done.

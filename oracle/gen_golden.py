@@ -241,6 +241,60 @@ def main():
     ent = ref.lu.categorical_entropy(torch.softmax(logits[0], dim=1))
     np.savez_compressed(os.path.join(OUT, "uncertainty.npz"), samples=_np(samp), var=_np(var),
                         logits=_np(logits), mutual_info=_np(mi), entropy=_np(ent))
+    # ---- final per-class detection filter (utils/filter_predictions.py) -----------------------
+    # The reference's own filter_and_draw_prep, K = 2 (Waymo vehicles; its uncertainty bookkeeping is
+    # only well-defined for one foreground class), image and lidar, with every UC flag on.
+    det = {}
+    g = torch.Generator().manual_seed(SEED + 60)
+    for tag, db_type, E in (("img", "image", 4), ("lid", "lidar", 7)):
+        cfg.NET_TYPE = db_type
+        R, K = 120, 2
+        for flag in ("EN_CLS_ALEATORIC", "EN_CLS_EPISTEMIC", "EN_BBOX_ALEATORIC", "EN_BBOX_EPISTEMIC"):
+            cfg.UC[flag] = True
+        probs = torch.softmax(torch.randn(R, K, generator=g) * 2.0, dim=1)
+        if db_type == "image":
+            ctr = torch.rand(R, 2, generator=g) * torch.tensor([1920.0, 1280.0])
+            ctr[R // 2:] = ctr[:R // 2] + torch.randn(R - R // 2, 2, generator=g) * 12      # overlapping clusters
+            wh = torch.exp(torch.rand(R, 2, generator=g) * 2.0 + 3.5)
+            one = torch.cat((ctr - wh / 2, ctr + wh / 2), dim=1) + torch.tensor([-30.0, -30.0, 40.0, 40.0]) * 0
+            one[:8] += torch.tensor([-200.0, -200.0, 300.0, 300.0])                        # some outside the frame
+            info = np.array([0, 1920, 0, 1280, 0, 0, 1.0], dtype=np.float32)
+        else:
+            ctr = torch.rand(R, 2, generator=g) * torch.tensor([700.0, 800.0])
+            ctr[R // 2:] = ctr[:R // 2] + torch.randn(R - R // 2, 2, generator=g) * 6
+            size = torch.tensor([47.3, 20.8, 1.77]) * (0.8 + 0.4 * torch.rand(R, 3, generator=g))
+            one = torch.cat((ctr, torch.rand(R, 1, generator=g) * 4, size, torch.rand(R, 1, generator=g) * 3 - 1.5), 1)
+            info = np.array([0, 700, 0, 800, 0, 12, 1.0], dtype=np.float32)
+        boxes = torch.cat((torch.zeros(R, E), one), dim=1)                                 # class 0 slot unused
+        uc = {"a_entropy": torch.rand(R, generator=g), "a_mutual_info": torch.rand(R, generator=g),
+              "a_cls_var": torch.rand(R, K, generator=g), "e_entropy": torch.rand(R, generator=g),
+              "e_mutual_info": torch.rand(R, generator=g), "e_cls_var": torch.rand(R, K, generator=g),
+              "a_bbox_var": torch.rand(R, K * E, generator=g), "e_bbox_var": torch.rand(R, K * E, generator=g)}
+        rois = torch.cat((torch.zeros(R, 1), torch.rand(R, 4, generator=g) * 500), dim=1)
+        r_np, all_boxes, all_uc = ref.fp.filter_and_draw_prep(rois, probs.clone(), boxes.clone(),
+                                                              {k: v.clone() for k, v in uc.items()}, info, K, 0.3,
+                                                              db_type)
+        det.update({f"{tag}_probs": _np(probs), f"{tag}_boxes": _np(boxes), f"{tag}_info": info,
+                    f"{tag}_rois": _np(rois), f"{tag}_out_rois": r_np, f"{tag}_dets": all_boxes[1]})
+        for k, v in uc.items():
+            det[f"{tag}_uc_{k}"] = _np(v)
+            det[f"{tag}_out_{k}"] = np.asarray(all_uc[1][k])
+        for flag in ("EN_CLS_ALEATORIC", "EN_CLS_EPISTEMIC", "EN_BBOX_ALEATORIC", "EN_BBOX_EPISTEMIC"):
+            cfg.UC[flag] = False
+    # the per-class call on its own, K = 4, thresholds as in test.py (0.1) -> dets / inds / keep per class
+    cfg.NET_TYPE = "image"
+    probs4 = torch.softmax(torch.randn(200, 4, generator=g) * 1.5, dim=1)
+    ctr = torch.rand(200, 2, generator=g) * torch.tensor([1242.0, 375.0])
+    ctr[100:] = ctr[:100] + torch.randn(100, 2, generator=g) * 8
+    wh = torch.exp(torch.rand(200, 2, generator=g) * 1.5 + 3.0)
+    b4 = torch.cat([torch.cat((ctr - wh / 2, ctr + wh / 2), dim=1) + torch.randn(200, 4, generator=g) * 3
+                    for _ in range(4)], dim=1)
+    det.update(k4_probs=_np(probs4), k4_boxes=_np(b4))
+    for c in range(1, 4):
+        d, inds, keep = ref.fp.nms_hstack_torch(probs4, b4, 0.1, c, 4, "image")
+        det[f"k4_dets{c}"], det[f"k4_inds{c}"], det[f"k4_keep{c}"] = d, _np(inds), np.asarray(keep)
+    np.savez_compressed(os.path.join(OUT, "detections.npz"), **det)
+
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

@@ -776,3 +776,66 @@ def sort_by_uncertainty(var: np.ndarray, descending=False) -> np.ndarray:
     to lower index first (``kind='stable'``; numpy's default quicksort is unstable)."""
     key = np.mean(var, axis=1) if var.ndim == 2 else var
     return np.argsort(-key if descending else key, kind="stable")
+
+
+# --------------------------------------------------------------------------------------
+# Final per-class detection filter  (utils/filter_predictions.py:23-130, model/test.py:213-221)
+# --------------------------------------------------------------------------------------
+def nms_hstack(scores: torch.Tensor, mean_boxes: torch.Tensor, thresh: float, c: int, bbox_elem: int, db_type: str,
+               nms_thresh: float = 0.6):
+    """utils/filter_predictions.py:45-72 (nms_hstack_torch) -> (cls_dets [m,E+1] np, inds, keep np)."""
+    inds = torch.where(scores[:, c] > thresh)[0]                                          # :46
+    if inds.shape[0] == 0:                                                               # :49-52
+        return np.empty(0), [], []
+    cls_scores = scores[inds, c]                                                          # :53
+    cls_boxes = mean_boxes[inds, c * bbox_elem:(c + 1) * bbox_elem]                       # :54
+    if db_type == "lidar":                                                               # :55-62
+        x1 = cls_boxes[:, 0:1] - cls_boxes[:, 3:4] / 2.0
+        y1 = cls_boxes[:, 1:2] - cls_boxes[:, 4:5] / 2.0
+        x2 = cls_boxes[:, 0:1] + cls_boxes[:, 3:4] / 2.0
+        y2 = cls_boxes[:, 1:2] + cls_boxes[:, 4:5] / 2.0
+        nms_boxes = torch.cat((x1, y1, x2, y2), dim=1)
+    else:
+        nms_boxes = cls_boxes
+    cls_dets = np.hstack((cls_boxes.numpy(), cls_scores.unsqueeze(1).numpy())).astype(np.float32, copy=False)  # :64
+    keep = nms(nms_boxes, cls_scores, nms_thresh).numpy()                                 # :66-69
+    return cls_dets[keep, :], inds, keep                                                  # :70-72
+
+
+def clamp_pred_boxes_image(pred_boxes: torch.Tensor, info, bbox_elem: int) -> torch.Tensor:
+    """utils/filter_predictions.py:77-91: clamp every class box to [0, w/scale - 1] x [0, h/scale - 1]."""
+    info = np.asarray(info, dtype=np.float32)
+    frame_width, frame_height, scale = info[1] - info[0], info[3] - info[2], info[6]
+    out = pred_boxes.clone()
+    out[:, 0::bbox_elem] = torch.clamp_min(out[:, 0::bbox_elem], 0)
+    out[:, 1::bbox_elem] = torch.clamp_min(out[:, 1::bbox_elem], 0)
+    out[:, 2::bbox_elem] = torch.clamp_max(out[:, 2::bbox_elem], float(frame_width / scale - 1))
+    out[:, 3::bbox_elem] = torch.clamp_max(out[:, 3::bbox_elem], float(frame_height / scale - 1))
+    return out
+
+
+def filter_detections(cls_score: torch.Tensor, pred_boxes: torch.Tensor, info, num_classes: int, bbox_elem: int,
+                      db_type: str, thresh: float = 0.1, nms_thresh: float = 0.6, max_dets: int = 0,
+                      uc_row: Optional[torch.Tensor] = None, uc_cls: Optional[torch.Tensor] = None):
+    """filter_and_draw_prep (:75-130) followed by the max-dets filter of model/test.py:213-221, per class,
+    with the uncertainty gathers of nms_hstack_var_torch (:23-43) applied to the ORIGINAL tensors for
+    every class (the reference re-uses the dict it has just overwritten, which only works for K = 2).
+    -> list over classes of dict(dets [m,E+1], roi [m] source roi, uc_row [m,U], uc_cls [m,U2,E])."""
+    boxes = clamp_pred_boxes_image(pred_boxes, info, bbox_elem) if db_type == "image" else pred_boxes
+    out = [None] * num_classes
+    for j in range(1, num_classes):
+        dets, inds, keep = nms_hstack(cls_score, boxes, thresh, j, bbox_elem, db_type, nms_thresh)
+        if len(keep) == 0:
+            out[j] = dict(dets=np.zeros((0, bbox_elem + 1), np.float32), roi=np.zeros(0, np.int64),
+                          uc_row=None, uc_cls=None)
+            continue
+        roi = inds.numpy()[keep]
+        if max_dets > 0 and len(dets) > max_dets:                                         # test.py:213-221
+            filter_thresh = np.sort(dets[:, -1])[-max_dets]
+            sel = np.where(dets[:, -1] >= filter_thresh)[0]
+            dets, roi = dets[sel, :], roi[sel]
+        out[j] = dict(dets=dets, roi=roi,
+                      uc_row=None if uc_row is None else uc_row.numpy()[roi],
+                      uc_cls=None if uc_cls is None else
+                      uc_cls.numpy()[roi][:, :, j * bbox_elem:(j + 1) * bbox_elem])
+    return out

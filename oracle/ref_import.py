@@ -3,7 +3,8 @@
 Used only by ``oracle/gen_golden.py`` and by the optional cross-check tests that
 skip when ``/root/reference`` is absent (it never exists on the GPU box).  Two
 modules the reference imports are not installed here; they are stubbed:
-``easydict`` (model/config.py:9) and ``matplotlib.pyplot`` (utils/loss_utils.py:7).
+``easydict`` (model/config.py:9), ``matplotlib.pyplot`` (utils/loss_utils.py:7) and ``cv2``
+(utils/filter_predictions.py:10, imported there but unused on the path).
 """
 import os
 import sys
@@ -48,6 +49,11 @@ def _install_stubs():
         mpl.pyplot = plt
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except ImportError:
+            sys.modules["cv2"] = types.ModuleType("cv2")
 
 
 def load():
@@ -70,6 +76,8 @@ def load():
     import layer_utils.proposal_target_layer as prt
     import utils.loss_utils as lu
     import utils.torchpoolers as tp
+    import utils.filter_predictions as fp
+    ns.fp = fp
     ns.cfg, ns.bt, ns.ub, ns.ga, ns.sn, ns.g3 = cfg, bt, ub, ga, sn, g3
     ns.pl, ns.ptl, ns.atl, ns.prt, ns.lu, ns.tp = pl, ptl, atl, prt, lu, tp
     return ns

@@ -64,6 +64,8 @@ def test_sass_is_sm100a_with_bulk_tma(built_lib):
     sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "UBLKCP" in sass, "plane-resident RoIAlign must load with 1-D bulk TMA"
+    assert "UTMALDG" in sass, "the rows RoIAlign kernel must fetch feature rows with tiled TMA"
+    assert "SYNCS" in sass and "CREDUX" in sass
 
 
 def test_product_never_imports_the_oracle():

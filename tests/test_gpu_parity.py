@@ -605,3 +605,91 @@ def test_variance_sort_is_stable_and_sorted():
         want = np.argsort(-k if desc else k, kind="stable")
         assert np.array_equal(order.cpu().numpy(), want)
         assert np.allclose(k, var.numpy().mean(1), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# final per-class detection filter (utils/filter_predictions.py, model/test.py:213-221)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,db_type", [("img", "image"), ("lid", "lidar")])
+def test_filter_and_draw_prep_golden(golden, tag, db_type):
+    """The reference's own filter_and_draw_prep output (all UC flags on, K = 2), bit for bit."""
+    from faster_rcnn_pytorch_multimodal_b200.utils.filter_predictions import filter_and_draw_prep
+    from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
+    g = golden("detections")
+    keys = ("a_entropy", "a_mutual_info", "a_cls_var", "e_entropy", "e_mutual_info", "e_cls_var", "a_bbox_var",
+            "e_bbox_var")
+    flags = ("EN_CLS_ALEATORIC", "EN_CLS_EPISTEMIC", "EN_BBOX_ALEATORIC", "EN_BBOX_EPISTEMIC")
+    old = {f: cfg.UC[f] for f in flags}
+    for f in flags:
+        cfg.UC[f] = True
+    try:
+        uc = {k: T(g[f"{tag}_uc_{k}"]) for k in keys}
+        rois, all_boxes, all_uc = filter_and_draw_prep(T(g[f"{tag}_rois"]), T(g[f"{tag}_probs"]), T(g[f"{tag}_boxes"]),
+                                                       uc, g[f"{tag}_info"], 2, 0.3, db_type)
+    finally:
+        for f in flags:
+            cfg.UC[f] = old[f]
+    assert np.array_equal(rois, g[f"{tag}_out_rois"])
+    assert all_boxes[1].dtype == np.float32 and np.array_equal(all_boxes[1], g[f"{tag}_dets"])
+    for k in keys:
+        assert np.array_equal(all_uc[1][k], g[f"{tag}_out_{k}"]), k
+
+
+def test_nms_hstack_torch_golden(golden):
+    from faster_rcnn_pytorch_multimodal_b200.utils.filter_predictions import nms_hstack_torch
+    g = golden("detections")
+    for c in range(1, 4):
+        dets, inds, keep = nms_hstack_torch(T(g["k4_probs"]), T(g["k4_boxes"]), 0.1, c, 4, "image")
+        assert np.array_equal(dets, g[f"k4_dets{c}"])
+        assert np.array_equal(inds.cpu().numpy(), g[f"k4_inds{c}"]) and np.array_equal(keep, g[f"k4_keep{c}"])
+
+
+@pytest.mark.parametrize("db_type,E", [("image", 4), ("lidar", 7)])
+def test_final_detections_batched(db_type, E):
+    """F frames x K classes in one launch vs the oracle per frame: ragged roi counts, max_dets with ties,
+    an empty class, uncertainty gathers."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    F, R, K, max_dets = 3, 300, 4, 20
+    g = torch.Generator().manual_seed(77)
+    probs = torch.softmax(torch.randn(F, R, K, generator=g) * 2.0, dim=2)
+    probs[:, :, 3] = 0.01                                   # class 3 never passes the threshold
+    probs[0, 10:40, 1] = 0.999                              # a run of tied top scores across the max_dets cut
+    if db_type == "image":
+        ctr = torch.rand(F, R, 1, 2, generator=g) * torch.tensor([1920.0, 1280.0])
+        wh = torch.exp(torch.rand(F, R, K, 2, generator=g) * 2.0 + 3.0)
+        boxes = torch.cat((ctr - wh / 2, ctr + wh / 2), dim=3)
+        boxes[:, :6] += torch.tensor([-300.0, -300.0, 400.0, 400.0])
+        info = torch.tensor([[0, 1920, 0, 1280, 0, 0, 1.0], [0, 1920, 0, 1280, 0, 0, 2.0], [10, 1000, 20, 700, 0, 0, 1.0]])
+    else:
+        ctr = torch.rand(F, R, 1, 2, generator=g) * torch.tensor([700.0, 800.0])
+        size = torch.tensor([47.3, 20.8, 1.77]) * (0.8 + 0.4 * torch.rand(F, R, K, 3, generator=g))
+        boxes = torch.cat((ctr.expand(F, R, K, 2), torch.rand(F, R, K, 1, generator=g), size,
+                           torch.rand(F, R, K, 1, generator=g)), dim=3)
+        info = torch.tensor([[0, 700, 0, 800, 0, 12, 1.0]]).repeat(F, 1)
+    boxes = boxes.reshape(F, R, K * E).contiguous()
+    num = torch.tensor([R, 157, 0], dtype=torch.int32)
+    uc_row = torch.rand(F, R, 3, generator=g)
+    uc_cls = torch.rand(F, R, 2, K * E, generator=g)
+    dets, det_roi, counts, o_row, o_cls = ops.final_detections(probs.to(dev()), boxes.to(dev()), info.to(dev()), E,
+                                                               db_type, 0.3, 0.6, max_dets=max_dets,
+                                                               num_rois=num.to(dev()), uc_row=uc_row.to(dev()),
+                                                               uc_cls=uc_cls.to(dev()))
+    dets, det_roi, counts, o_row, o_cls = (t.cpu() for t in (dets, det_roi, counts, o_row, o_cls))
+    for f in range(F):
+        n = int(num[f])
+        want = O.filter_detections(probs[f, :n], boxes[f, :n], info[f].numpy(), K, E, db_type, thresh=0.3, nms_thresh=0.6,
+                                   max_dets=max_dets, uc_row=uc_row[f, :n], uc_cls=uc_cls[f, :n])
+        assert int(counts[f, 0]) == 0
+        for c in range(1, K):
+            m = int(counts[f, c])
+            w = want[c]
+            assert m == len(w["dets"]), (f, c, m, len(w["dets"]))
+            assert np.array_equal(dets[f, c, :m].numpy(), w["dets"])
+            assert float(dets[f, c, m:].abs().sum()) == 0.0 and bool((det_roi[f, c, m:] == -1).all())
+            if m:
+                # ties (equal scores) may be ordered differently by torchvision's unstable sort: compare as sets there
+                assert sorted(det_roi[f, c, :m].tolist()) == sorted(w["roi"].tolist())
+                assert np.array_equal(o_row[f, c, :m].numpy(), uc_row[f][det_roi[f, c, :m].long()].numpy())
+                got_cls = o_cls[f, c, :m].view(m, 2, E).numpy()
+                assert np.array_equal(got_cls, uc_cls[f][det_roi[f, c, :m].long()][:, :, c * E:(c + 1) * E].numpy())
+    assert int(counts[0, 1]) > max_dets                     # the tie run extends the cut

@@ -169,3 +169,38 @@ def test_uncertainty(golden):
     v = g["var"]
     order = O.sort_by_uncertainty(v, descending=True)
     assert np.all(np.diff(v.mean(1)[order]) <= 0)
+
+
+# ------------------------------------------------------------------------------------------
+# final per-class detection filter (utils/filter_predictions.py), pinned by the reference's own output
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,db_type,E", [("img", "image", 4), ("lid", "lidar", 7)])
+def test_filter_detections_matches_reference(golden, tag, db_type, E):
+    g = golden("detections")
+    uc_row = torch.from_numpy(np.concatenate([g[f"{tag}_uc_a_entropy"][:, None], g[f"{tag}_uc_a_mutual_info"][:, None],
+                                              g[f"{tag}_uc_a_cls_var"]], axis=1))
+    uc_cls = torch.from_numpy(np.stack([g[f"{tag}_uc_a_bbox_var"], g[f"{tag}_uc_e_bbox_var"]], axis=1))
+    out = O.filter_detections(torch.from_numpy(g[f"{tag}_probs"]), torch.from_numpy(g[f"{tag}_boxes"]),
+                              g[f"{tag}_info"], 2, E, db_type, thresh=0.3, nms_thresh=0.6, uc_row=uc_row, uc_cls=uc_cls)
+    d = out[1]
+    assert np.array_equal(d["dets"], g[f"{tag}_dets"])
+    assert np.array_equal(d["uc_row"][:, 0:1], g[f"{tag}_out_a_entropy"])
+    assert np.array_equal(d["uc_row"][:, 1:2], g[f"{tag}_out_a_mutual_info"])
+    assert np.array_equal(d["uc_row"][:, 2:], g[f"{tag}_out_a_cls_var"])
+    assert np.array_equal(d["uc_cls"][:, 0], g[f"{tag}_out_a_bbox_var"])
+    assert np.array_equal(d["uc_cls"][:, 1], g[f"{tag}_out_e_bbox_var"])
+
+
+def test_nms_hstack_matches_reference(golden):
+    g = golden("detections")
+    for c in range(1, 4):
+        dets, inds, keep = O.nms_hstack(torch.from_numpy(g["k4_probs"]), torch.from_numpy(g["k4_boxes"]), 0.1, c, 4,
+                                        "image", 0.6)
+        assert np.array_equal(dets, g[f"k4_dets{c}"])
+        assert np.array_equal(np.asarray(inds), g[f"k4_inds{c}"]) and np.array_equal(keep, g[f"k4_keep{c}"])
+    # max-dets filter (model/test.py:213-221) on the same rows
+    out = O.filter_detections(torch.from_numpy(g["k4_probs"]), torch.from_numpy(g["k4_boxes"]),
+                              np.array([0, 1e9, 0, 1e9, 0, 0, 1], np.float32), 4, 4, "image",
+                              thresh=0.1, nms_thresh=0.6, max_dets=5)
+    for c in range(1, 4):
+        assert len(out[c]["dets"]) == min(5, len(g[f"k4_dets{c}"]))
