@@ -25,6 +25,10 @@ namespace b2d {
 
 size_t sweep_workspace_bytes(int F, int H, int n_list, int per_frame);
 size_t rows_workspace_bytes(int F, int H, int per_frame);
+size_t bwd_rows_workspace_bytes(int n_list);
+int roi_align_backward_rows(int F, int C, int H, int W, const float* grad_out, const RoiList& L, int PH, int PW,
+                            float scale, int S, int aligned, int accumulate, float* grad_feat, void* workspace,
+                            size_t workspace_bytes, cudaStream_t st);
 int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
                            float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
                            cudaStream_t st);
@@ -288,7 +292,8 @@ extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W
   if (F <= 0 || H <= 0 || num_rois <= 0) return 0;
   if (per_frame <= 0 || per_frame > num_rois) per_frame = num_rois;
   const size_t a = sweep_workspace_bytes(F, H, num_rois, per_frame), b = rows_workspace_bytes(F, H, per_frame);
-  return a > b ? a : b;
+  const size_t c = bwd_rows_workspace_bytes(num_rois);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
@@ -342,13 +347,19 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
 extern "C" int b2d_roi_align_backward(int F, int C, int H, int W, const float* grad_out, const float* rois,
                                       int num_rois, const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count,
                                       int seg_stride, int PH, int PW, float spatial_scale, int sampling_ratio,
-                                      int aligned, int accumulate, float* grad_feat, void* /*workspace*/,
-                                      size_t /*workspace_bytes*/, void* stream) {
+                                      int aligned, int accumulate, float* grad_feat, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   if (F <= 0 || C <= 0 || H <= 0 || W <= 0 || PH <= 0 || PW <= 0 || !grad_feat) return B2D_ERR_INVALID_ARG;
   RoiList L{rois, roi_ids, roi_ids ? n_roi_ids : num_rois, seg_count, seg_stride};
   if (seg_count && (seg_stride <= 0 || (long long)seg_stride * F > L.n)) return B2D_ERR_INVALID_ARG;
   if (L.n > 0 && (!rois || !grad_out)) return B2D_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  {
+    // production path: table-driven one-warp-per-row kernel (roi_align_bwd_rows.cu); needs the workspace
+    const int rc = roi_align_backward_rows(F, C, H, W, grad_out, L, PH, PW, spatial_scale, sampling_ratio, aligned,
+                                           accumulate, grad_feat, workspace, workspace_bytes, st);
+    if (rc != B2D_ERR_UNSUPPORTED) return rc;
+  }
   const size_t row_bytes = (size_t)W * kBwdPad * sizeof(float);
   int band = (int)((200 * 1024) / row_bytes);
   if (band < 1) return B2D_ERR_UNSUPPORTED;   // W > ~1500: needs column tiling

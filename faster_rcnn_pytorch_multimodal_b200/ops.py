@@ -172,10 +172,14 @@ def _roi_align_backward(grad_out, rois, feat_shape, out_hw, scale, sampling_rati
     if rois.shape[0] == 0 or (roi_ids is not None and roi_ids.numel() == 0):
         return grad_feat if accumulate else grad_feat.zero_()
     n_ids = 0 if roi_ids is None else roi_ids.numel()
-    check(lib().b2d_roi_align_backward(Fr, Cc, H, W, ptr(grad_out), ptr(rois), rois.shape[0], ptr(roi_ids), n_ids,
-                                       ptr(seg_count), int(seg_stride), out_hw[0], out_hw[1], float(scale),
-                                       int(sampling_ratio), int(bool(aligned)), int(accumulate), ptr(grad_feat),
-                                       None, 0, stream_ptr(grad_out.device)), "b2d_roi_align_backward")
+    L = lib()
+    n_list = n_ids if roi_ids is not None else rois.shape[0]
+    per_frame = int(seg_stride) if seg_count is not None else n_list
+    ws = workspaces.get(grad_out.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, n_list, per_frame))
+    check(L.b2d_roi_align_backward(Fr, Cc, H, W, ptr(grad_out), ptr(rois), rois.shape[0], ptr(roi_ids), n_ids,
+                                   ptr(seg_count), int(seg_stride), out_hw[0], out_hw[1], float(scale),
+                                   int(sampling_ratio), int(bool(aligned)), int(accumulate), ptr(grad_feat),
+                                   ptr(ws), ws.numel(), stream_ptr(grad_out.device)), "b2d_roi_align_backward")
     return grad_feat
 
 
