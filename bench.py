@@ -155,8 +155,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="independent frames per step per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=8, help="frames per host-buffer call")
+    ap.add_argument("--frames", type=int, default=128, help="independent frames per step per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=16, help="frames per host-buffer call")
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--cpu-baseline-frames", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
