@@ -27,7 +27,10 @@ constexpr int kCh = 32;
 constexpr int kP = 7;
 constexpr int kTabVec = 2 * kP * 2 + 1;   // float4 per RoI: 14 sample rows, 14 sample columns, 1 header
 constexpr int kMaxWarps = 16;
-constexpr int kTile = 4;                  // RoI tiles per batch (two batches in flight)
+#ifndef B2D_BWD_TILE
+#define B2D_BWD_TILE 4
+#endif
+constexpr int kTile = B2D_BWD_TILE;                  // RoI tiles per batch (two batches in flight)
 constexpr int kTileWords = kCh * kP * kP; // 1568 floats = 6272 bytes
 
 struct Plan {

@@ -21,5 +21,5 @@ for it in range(3):
     e1.record(); torch.cuda.synchronize()
     L.b2d_rows_debug(out, 0)
     v = list(out)
-    ncons = 10 * 32 * F
+    ncons = 8 * 32 * F
     print(f"ms {e0.elapsed_time(e1):.3f} per consumer-warp avg cycles: total {v[0]/ncons:.0f} wait_full {v[1]/ncons:.0f} wait_done {v[2]/ncons:.0f} run_item {v[3]/ncons:.0f} fetch(prod) {v[4]/(64*F):.0f} ri_setup {v[8]/ncons:.0f} ri_rows {v[9]/ncons:.0f} ri_out {v[10]/ncons:.0f} | producer: total {v[7]/(64*F):.0f} wait_done {v[5]/(64*F):.0f} wait_stg {v[6]/(64*F):.0f}")
