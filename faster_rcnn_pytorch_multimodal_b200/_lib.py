@@ -11,7 +11,7 @@ import threading
 import torch  # noqa: F401  (loads libcudart before our library resolves it)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2dglue.so")
+LIB_PATH = os.environ.get("B2D_LIB_PATH") or os.path.join(_HERE, "libb2dglue.so")   # override: A/B builds only
 
 _f = C.c_void_p      # device / host float*
 _i = C.c_void_p      # int32_t* / int64_t*

@@ -99,12 +99,13 @@ struct Plan {
 static Plan make_plan(int H, int W, bool allow_tma) {
   Plan p{};
   p.fill = (allow_tma && W % 4 == 0) ? 1 : 0;
-  const int pitch = ((W + 1 + 30) / 32) * 32 + 1;    // smallest value = 1 (mod 32) that is >= W + 1
+  const int pitch = (W + 1) | 1;                     // smallest ODD value >= W + 1: any odd pitch maps 32 channels to 32 banks
   p.lane_stride = pitch;
   p.row_words = kCh * pitch;
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * W * 4 : 0;
-  const size_t fixed = (size_t)kWarps * kRecBytes + (size_t)kWarps * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging;
+  const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and an output tile
+  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging;
   const size_t budget = 227 * 1024 - 2048;
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
@@ -343,6 +344,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// 1-D bulk copy shared -> global (16-byte aligned on both sides), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ float lds_at(uint32_t addr) {
   float v;
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));   // not volatile: taps of an item may reorder
@@ -457,7 +465,10 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   __shared__ int s_ctr;
   __shared__ int s_progress[kWarps];                    // TMA fill: bucket each consumer warp is working in
   constexpr int kConsumers = FILL ? kWarps - kProducers : kWarps;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp-uniform for ptxas: with a per-thread warp index the producer branch below looks divergent and
+  // every tap address of the consumers is rebuilt with an IADD instead of [column + uniform row] addressing
+  const int warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(tid >> 5));
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * kCh;
   const int C = a.C, H = a.H, W = a.W;
@@ -473,8 +484,8 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   // turn every slot / staging access into a generic load)
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
-  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)warp * B2D_OUT_TILES * kCh * kP;
-  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kWarps * kRecBytes / 4 + (size_t)kWarps * B2D_OUT_TILES * kCh * kP;
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * B2D_OUT_TILES * kCh * kP;
+  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * B2D_OUT_TILES * kCh * kP;
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
   if (tid == 0) {
