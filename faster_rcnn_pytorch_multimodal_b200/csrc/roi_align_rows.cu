@@ -96,14 +96,19 @@ struct Plan {
   bool ok;
 };
 
+// Width of a staged row.  A tiled-TMA box must start on a 16-byte boundary of the plane, so when W is not a
+// multiple of 4 the box starts up to 3 elements before the row and is 4 elements wider; the repack reads it
+// with that per-row shift.
+static int stage_width(int W) { return W % 4 == 0 ? W : (W + 3) / 4 * 4 + 4; }
+
 static Plan make_plan(int H, int W, bool allow_tma) {
   Plan p{};
-  p.fill = (allow_tma && W % 4 == 0) ? 1 : 0;
+  p.fill = (allow_tma && (H * W) % 4 == 0 && stage_width(W) <= 256) ? 1 : 0;
   const int pitch = (W + 1) | 1;                     // smallest ODD value >= W + 1: any odd pitch maps 32 channels to 32 banks
   p.lane_stride = pitch;
   p.row_words = kCh * pitch;
   const size_t row_bytes = (size_t)p.row_words * 4;
-  const size_t staging = p.fill ? (size_t)kStages * kCh * W * 4 : 0;
+  const size_t staging = p.fill ? (size_t)kStages * kCh * stage_width(W) * 4 : 0;
   const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and an output tile
   const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging;
   const size_t budget = 227 * 1024 - 2048;
@@ -448,7 +453,7 @@ struct KArgs {
   const float* feat;
   RoiList L;
   int C, H, W;
-  int lane_stride, row_words;
+  int lane_stride, row_words, stage_w;
   int St, nblk, nbk, nsteps, items_cap, nostore;
   Ws ws;
   float* out;
@@ -513,7 +518,8 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     DBG_T0(tp);
-    const uint32_t row_tx = (uint32_t)kCh * (uint32_t)W * 4u;     // the box is always 32 planes (OOB planes zero-filled)
+    const int Ws = a.stage_w;                                     // staged row width (>= W, multiple of 4)
+    const uint32_t row_tx = (uint32_t)kCh * (uint32_t)Ws * 4u;    // the box is always 32 planes (OOB planes / elements zero-filled)
     const int nchunk = (W + 31) / 32;
     const bool tail_ok = lane + 32 * (nchunk - 1) < W;
     const int plane0 = f * C + c0;
@@ -523,7 +529,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       if (pw_id == 0 && lane == 0) {
         uint64_t* bar = &stg_bar[y % kStages];
         mbar_expect_tx(bar, row_tx);
-        tma_load_2d(smem_u32(stg + (size_t)(y % kStages) * kCh * W), &tmap, y * W, plane0, bar);
+        tma_load_2d(smem_u32(stg + (size_t)(y % kStages) * kCh * Ws), &tmap, (y * W) & ~3, plane0, bar);
       }
     };
     for (int y = 0; y < kStages && y < H; ++y) fetch(y);
@@ -547,8 +553,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
         mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
         DBG_ACC(6, t2);
       }
-      const uint32_t sstep = (uint32_t)W * 4u, dstep = (uint32_t)a.lane_stride * 4u;
-      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * W) + (uint32_t)lane * 4u + (uint32_t)(pw_id * kChP) * sstep;
+      const uint32_t sstep = (uint32_t)Ws * 4u, dstep = (uint32_t)a.lane_stride * 4u;
+      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * Ws) + (uint32_t)(lane + ((y * W) & 3)) * 4u +
+                     (uint32_t)(pw_id * kChP) * sstep;
       uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
                      (uint32_t)(pw_id * kChP) * dstep;
       // 8 channels x up to 4 chunks (32 values) in flight per lane
@@ -799,10 +806,10 @@ static EncodeTiledFn encode_tiled_fn() {
 // feature planes as a 2-D tensor [F*C planes][H*W elements]; box = one row of 32 consecutive planes
 static bool make_tmap(CUtensorMap* map, const float* feat, int F, int C, int H, int W) {
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || (reinterpret_cast<uintptr_t>(feat) & 15u) || W % 4 != 0 || W > 256) return false;
+  if (!enc || (reinterpret_cast<uintptr_t>(feat) & 15u) || ((size_t)H * W) % 4 != 0 || stage_width(W) > 256) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)H * W, (cuuint64_t)F * C};
   const cuuint64_t strides[1] = {(cuuint64_t)H * W * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)kCh};
+  const cuuint32_t box[2] = {(cuuint32_t)stage_width(W), (cuuint32_t)kCh};
   const cuuint32_t estr[2] = {1u, 1u};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -851,7 +858,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   while (split < 4 && groups * split < 2 * kNumSMs) split *= 2;
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
-  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
     prep_kernel<SS><<<F, 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max,        \
