@@ -59,7 +59,19 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #endif
 
 #ifndef B2D_STAGES
-#define B2D_STAGES 3
+#define B2D_STAGES 2
+#endif
+#ifndef B2D_ROW_UNROLL
+#define B2D_ROW_UNROLL 1
+#endif
+#ifndef B2D_TAP_PIPE
+#define B2D_TAP_PIPE 0
+#endif
+#ifndef B2D_TAP_PIPE_MAX_NPH
+#define B2D_TAP_PIPE_MAX_NPH 4
+#endif
+#ifndef B2D_NARROW
+#define B2D_NARROW 0
 #endif
 #ifndef B2D_OUT_TILES
 #define B2D_OUT_TILES 1
@@ -73,6 +85,7 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #ifndef B2D_WARPS
 #define B2D_WARPS 10
 #endif
+constexpr int kRowUnroll = B2D_ROW_UNROLL;   // row loop of an item: 1 keeps the 14 item variants inside the instruction cache
 constexpr int kWarps = B2D_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
@@ -84,8 +97,19 @@ constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 
+#ifndef B2D_POOL
+#define B2D_POOL 2
+#endif
+constexpr int kPool = B2D_POOL;             // TMA fill: whole-RoI output tiles [32 ch][49] shared by the consumer warps
+constexpr int kTileWords = kCh * kP * kP;
 constexpr int kStages = B2D_STAGES;         // staging rows of the TMA fill
-constexpr int kProducers = 2;      // producer warps of the TMA fill (each repacks 32 / kProducers channels)
+#ifndef B2D_PRODUCERS
+#define B2D_PRODUCERS 2
+#endif
+#ifndef B2D_REPACK_PIPE
+#define B2D_REPACK_PIPE 0
+#endif
+constexpr int kProducers = B2D_PRODUCERS;   // producer warps of the TMA fill (each repacks 32 / kProducers channels)
 
 struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
@@ -110,8 +134,9 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * stage_width(W) * 4 : 0;
   const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and an output tile
-  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging;
-  const size_t budget = 227 * 1024 - 2048;
+  const size_t pool = p.fill ? (size_t)kPool * kTileWords * 4 : 0;
+  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging + pool;
+  const size_t budget = 227 * 1024 - 1280;       // 1.2 KB of static shared memory (barriers, locks, counters)
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
   if (Rr >= H) {
@@ -190,8 +215,9 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 }
 
 // Record of one item (float4 units):
-//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16, bucket, -}
+//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16 | narrow << 17, bucket, -}
 //   [1..11]   14 column taps x 3 words {byte offset of the lo column, hx, lx}; the hi column is lo + 1
+//             (narrow items, code bit 17: [1..7] = 7 bins x {byte offset of the base column, w0, w1, w2})
 //   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 3);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
 template <int S>
@@ -253,22 +279,54 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
       // column taps.  Invalid samples carry zero weights and point at column 0 (always resident);
       // at the clamped right border lx is 0 and the hi tap reads whatever follows the row (finite).
       float* xw = reinterpret_cast<float*>(rec + 1);
-      for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
-        int xo = 0;
-        float hx = 0.0f, lx = 0.0f;
-        if (k < kP * S) {
-          const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
-          if (t.ok) {
-            xo = t.lo * 4;
-            hx = t.wlo;
-            lx = t.whi;
+      // "narrow" items (S == 2): the two samples of every bin fall within three consecutive pixel columns
+      // (bins up to two pixels wide), so the bin needs 3 taps per row {base, base+1, base+2} with merged
+      // weights instead of 4: record = 7 x {byte offset of base, w0, w1, w2}.
+      bool narrow = B2D_NARROW && S == 2 && W >= 3;
+      if (narrow) {
+        for (int pw = 0; pw < kP; ++pw) {
+          int base = W, top = -1;
+          AxisTap t[2];
+          for (int ix = 0; ix < 2; ++ix) {
+            t[ix] = axis_tap(g.start_w, g.bin_w, pw, ix, S, W);
+            if (t[ix].ok) {
+              base = min(base, t[ix].lo);
+              top = max(top, t[ix].hi);
+            }
           }
+          if (top < 0) base = 0;
+          if (top - base > 2) narrow = false;
+          base = min(base, W - 2);                       // base + 2 <= W: the zeroed pad column at worst
+          float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          for (int ix = 0; ix < 2; ++ix)
+            if (t[ix].ok) {
+              w[min(t[ix].lo - base, 3)] += t[ix].wlo;
+              w[min(t[ix].hi - base, 3)] += t[ix].whi;
+            }
+          xw[4 * pw] = __int_as_float(base * 4);
+          xw[4 * pw + 1] = w[0];
+          xw[4 * pw + 2] = w[1];
+          xw[4 * pw + 3] = w[2];
         }
-        xw[3 * k] = __int_as_float(xo);
-        xw[3 * k + 1] = hx;
-        xw[3 * k + 2] = lx;
       }
-      xw[42] = xw[43] = 0.0f;
+      if (!narrow) {
+        for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
+          int xo = 0;
+          float hx = 0.0f, lx = 0.0f;
+          if (k < kP * S) {
+            const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
+            if (t.ok) {
+              xo = t.lo * 4;
+              hx = t.wlo;
+              lx = t.whi;
+            }
+          }
+          xw[3 * k] = __int_as_float(xo);
+          xw[3 * k + 1] = hx;
+          xw[3 * k + 2] = lx;
+        }
+        xw[42] = xw[43] = 0.0f;
+      }
       // distinct feature rows of the item and their weights per bin-row
       int nrows = 0;
       if (!slow) {
@@ -293,14 +351,14 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
             }
           }
         }
-        const int rv = nph > 3 ? 2 : 1;
+        const int rv = nph > 2 ? 2 : 1;              // matches the NPH variant the item runs on (2, 4 or 7)
         for (int j = 0; j < nrows; ++j) {
           const int off = (row_id[j] % Rr) * row_bytes;
           rec[kRowVec0 + j * rv] = make_float4(__int_as_float(off), wy[j][0], wy[j][1], wy[j][2]);
           if (rv == 2) rec[kRowVec0 + j * rv + 1] = make_float4(wy[j][3], wy[j][4], wy[j][5], wy[j][6]);
         }
       }
-      const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
+      const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16) | ((narrow ? 1 : 0) << 17);
       rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(b), 0.f);
     });
   }
@@ -356,6 +414,30 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Output tile pool of the TMA variant: kPool whole-RoI tiles [32 ch][49].  A whole-RoI item of a full channel
+// group TRIES to take a tile (one pass over the locks, no waiting): with a tile the 49 values of each lane go
+// to shared memory once and leave with ONE bulk store of 6272 contiguous bytes - no LDS/STG round trip; the
+// tile stays locked until the copy has read it (released at the warp's next item).  Without one the item
+// takes the regular bin-row path.
+__device__ __forceinline__ int tile_try_acquire(int* locks, int warp, int lane) {
+  unsigned t = 0;                          // tile index + 1, 0 = none
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kPool; ++k) {
+      const int i = (warp + k) % kPool;
+      if (t == 0 && atomicCAS(&locks[i], 0, 1) == 0) t = (unsigned)i + 1u;
+    }
+  }
+  return (int)__reduce_max_sync(0xffffffffu, t) - 1;
+}
+__device__ __forceinline__ void tile_release(int* locks, int t, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(&locks[t]) = 0;
+  }
+}
+
 __device__ __forceinline__ float lds_at(uint32_t addr) {
   float v;
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));   // not volatile: taps of an item may reorder
@@ -363,15 +445,28 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 }
 
 // One item: nph = NPH bin-rows of one RoI for this lane's channel.
-template <int NPH, int S, class AfterRows>
-__device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, uint32_t lane_base,
+// NPH is the variant (2, 4 or 7 accumulator rows), nph <= NPH the bin-rows the item really has: the rows in
+// between carry zero weights and are not stored.  (One variant per nph, times narrow / wide, does not fit
+// the instruction cache: the 14-variant build was 12 % slower.)
+template <int NPH, int S, bool NARROW, bool POOL, class AfterRows>
+__device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
-                                         const int (&ooff)[kP], unsigned omask, AfterRows after_rows) {
-  constexpr int NX = kP * S;
-  constexpr int RV = NPH > 3 ? 2 : 1;
+                                         const int (&ooff)[kP], unsigned omask, float* __restrict__ pool, int* locks,
+                                         int warp, bool tile_out, int& held, AfterRows after_rows) {
+  constexpr int NX = NARROW ? kP : kP * S;
+  constexpr int RV = NPH > 2 ? 2 : 1;
   uint32_t xa[NX];
-  float lx[NX], hx[NX];
-  {
+  float lx[NX], hx[NX], mx[NARROW ? NX : 1];
+  if (NARROW) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+      const float4 t = slot[1 + k];
+      xa[k] = lane_base + (uint32_t)__float_as_int(t.x);
+      hx[k] = t.y;
+      mx[k] = t.z;
+      lx[k] = t.w;
+    }
+  } else {
     float q[4 * kXVec];
 #pragma unroll
     for (int v = 0; v < kXVec; ++v) {
@@ -394,49 +489,122 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) acc[p][pw] = 0.0f;
 
-  // row entries are fetched one row ahead so that the LDS -> CREDUX -> tap-address chain of row i + 1
-  // overlaps the taps of row i (reading one entry past the last row stays inside shared memory)
-  float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + (RV == 2 ? 1 : 0)];
-  for (int i = 0; i < nrows; ++i) {
-    float wy[kP];
-    wy[0] = e0.y;
-    wy[1] = e0.z;
-    wy[2] = e0.w;
-    if (RV == 2) {
-      wy[3] = e1.x;
-      wy[4] = e1.y;
-      wy[5] = e1.z;
-      wy[6] = e1.w;
-    }
-    // the row offset is the same in every lane; the reduction tells ptxas so (CREDUX -> uniform
-    // register), which lets the taps below use [column + uniform row + imm] addressing
-    const uint32_t ro = __reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(e0.x));
-    e0 = slot[kRowVec0 + (i + 1) * RV];
-    if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
+  constexpr int NT = NARROW ? 3 * kP : 2 * S * kP;      // taps per feature row
+  auto load_row = [&](float (&t)[NT], uint32_t ro) {
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
-      float t;
-      if (S == 2) {
-        const float a = lds_at(xa[2 * pw] + ro), b = lds_at(xa[2 * pw] + ro + 4);
-        const float c = lds_at(xa[2 * pw + 1] + ro), d = lds_at(xa[2 * pw + 1] + ro + 4);
-        t = hx[2 * pw] * a;
-        t = fmaf(lx[2 * pw], b, t);
-        t = fmaf(hx[2 * pw + 1], c, t);
-        t = fmaf(lx[2 * pw + 1], d, t);
+      if (NARROW) {
+        t[3 * pw] = lds_at(xa[pw] + ro);
+        t[3 * pw + 1] = lds_at(xa[pw] + ro + 4);
+        t[3 * pw + 2] = lds_at(xa[pw] + ro + 8);
+      } else if (S == 2) {
+        t[4 * pw] = lds_at(xa[2 * pw] + ro);
+        t[4 * pw + 1] = lds_at(xa[2 * pw] + ro + 4);
+        t[4 * pw + 2] = lds_at(xa[2 * pw + 1] + ro);
+        t[4 * pw + 3] = lds_at(xa[2 * pw + 1] + ro + 4);
       } else {
-        const float a = lds_at(xa[pw] + ro), b = lds_at(xa[pw] + ro + 4);
-        t = hx[pw] * a;
-        t = fmaf(lx[pw], b, t);
+        t[2 * pw] = lds_at(xa[pw] + ro);
+        t[2 * pw + 1] = lds_at(xa[pw] + ro + 4);
+      }
+    }
+  };
+  auto compute_row = [&](const float (&t)[NT], const float4& f0, const float4& f1) {
+    float wy[kP];
+    wy[0] = f0.y;
+    wy[1] = f0.z;
+    wy[2] = f0.w;
+    if (RV == 2) {
+      wy[3] = f1.x;
+      if (NPH > 4) {
+        wy[4] = f1.y;
+        wy[5] = f1.z;
+        wy[6] = f1.w;
+      }
+    }
+#pragma unroll
+    for (int pw = 0; pw < kP; ++pw) {
+      float v;
+      if (NARROW) {
+        v = hx[pw] * t[3 * pw];
+        v = fmaf(mx[pw], t[3 * pw + 1], v);
+        v = fmaf(lx[pw], t[3 * pw + 2], v);
+      } else if (S == 2) {
+        v = hx[2 * pw] * t[4 * pw];
+        v = fmaf(lx[2 * pw], t[4 * pw + 1], v);
+        v = fmaf(hx[2 * pw + 1], t[4 * pw + 2], v);
+        v = fmaf(lx[2 * pw + 1], t[4 * pw + 3], v);
+      } else {
+        v = hx[pw] * t[2 * pw];
+        v = fmaf(lx[pw], t[2 * pw + 1], v);
       }
 #pragma unroll
-      for (int p = 0; p < NPH; ++p) acc[p][pw] = fmaf(wy[p], t, acc[p][pw]);
+      for (int p = 0; p < NPH; ++p) acc[p][pw] = fmaf(wy[p], v, acc[p][pw]);
+    }
+  };
+  // The row offset is the same in every lane; the reduction tells ptxas so (CREDUX -> uniform register),
+  // which lets the taps use [column + uniform row + imm] addressing.  Reading row entries past the last
+  // row stays inside shared memory; such entries are never used as addresses.
+  auto row_off = [](const float4& f0) { return __reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(f0.x)); };
+  constexpr int R1 = RV == 2 ? 1 : 0;
+  if (B2D_TAP_PIPE && NPH <= B2D_TAP_PIPE_MAX_NPH) {
+    // software pipeline: the taps of row i + 1 are in flight while row i is contracted (two register sets),
+    // row entries run two rows ahead so the LDS -> CREDUX -> tap-address chain is off the critical path
+    float ta[NT], tb[NT];
+    float4 a0 = slot[kRowVec0], a1 = slot[kRowVec0 + R1];
+    float4 b0 = slot[kRowVec0 + RV], b1 = slot[kRowVec0 + RV + R1];
+    load_row(ta, row_off(a0));
+    for (int i = 0; i < nrows; i += 2) {
+      const bool has_b = i + 1 < nrows;
+      const float4 c0 = slot[kRowVec0 + (i + 2) * RV], c1 = slot[kRowVec0 + (i + 2) * RV + R1];
+      if (has_b) load_row(tb, row_off(b0));
+      compute_row(ta, a0, a1);
+      if (!has_b) break;
+      const float4 d0 = slot[kRowVec0 + (i + 3) * RV], d1 = slot[kRowVec0 + (i + 3) * RV + R1];
+      if (i + 2 < nrows) load_row(ta, row_off(c0));
+      compute_row(tb, b0, b1);
+      a0 = c0;
+      a1 = c1;
+      b0 = d0;
+      b1 = d1;
+    }
+  } else {
+    // row entries are fetched one row ahead so that the LDS -> CREDUX -> tap-address chain of row i + 1
+    // overlaps the taps of row i
+    float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + R1];
+#pragma unroll kRowUnroll
+    for (int i = 0; i < nrows; ++i) {
+      const float4 f0 = e0, f1 = e1;
+      const uint32_t ro = row_off(f0);
+      e0 = slot[kRowVec0 + (i + 1) * RV];
+      if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
+      float t[NT];
+      load_row(t, ro);
+      compute_row(t, f0, f1);
     }
   }
   after_rows();      // the ring is not needed any more: lets the caller release it early
+  if (POOL && NPH == kP && kPool > 0) {
+    if (tile_out && nph == kP) {
+      const int t = tile_try_acquire(locks, warp, lane);
+      if (t >= 0) {
+        float* tile = pool + (size_t)t * kTileWords;
+#pragma unroll
+        for (int p = 0; p < NPH; ++p)
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) tile[lane * (kP * kP) + p * kP + pw] = acc[p][pw];   // 49 words per lane: odd pitch
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
+        __syncwarp();
+        if (lane == 0) bulk_s2g(o, smem_u32(tile), (uint32_t)kTileWords * 4u);
+        held = t;
+        return;
+      }
+    }
+  }
   // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw); two
   // tiles alternate, so the shared-memory round trip of bin-row p overlaps the staging of p + 1
 #pragma unroll
   for (int p = 0; p < NPH; ++p) {
+    if (p >= nph) break;
     float* tile = stage + (B2D_OUT_TILES > 1 ? (p & 1) * (kCh * kP) : 0);
     if (B2D_OUT_TILES == 1 && p > 0) __syncwarp();
 #pragma unroll
@@ -468,6 +636,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every consumer warp is past bucket j
   __shared__ __align__(8) uint64_t stg_bar[kStages];    // staging row landed (TMA bytes)
   __shared__ int s_ctr;
+  __shared__ int s_tile_lock[kPool > 0 ? kPool : 1];
   __shared__ int s_progress[kWarps];                    // TMA fill: bucket each consumer warp is working in
   constexpr int kConsumers = FILL ? kWarps - kProducers : kWarps;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -490,9 +659,11 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
   float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * B2D_OUT_TILES * kCh * kP;
-  float* stg = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * B2D_OUT_TILES * kCh * kP;
+  float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * B2D_OUT_TILES * kCh * kP;
+  float* stg = pool + (size_t)kPool * kTileWords;
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
+  if (tid < kPool) s_tile_lock[tid] = 0;
   if (tid == 0) {
     s_ctr = 0;
     for (int i = 0; i < kStages; ++i) mbar_init(&stg_bar[i], 1);
@@ -558,29 +729,46 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
                      (uint32_t)(pw_id * kChP) * sstep;
       uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
                      (uint32_t)(pw_id * kChP) * dstep;
-      // 8 channels x up to 4 chunks (32 values) in flight per lane
-      for (int c8 = 0; c8 < kChP; c8 += 8) {
-        for (int cg = 0; cg < nchunk; cg += 4) {
-          float v[32];
+      // batches of 8 channels x up to 4 chunks (32 values per lane); with B2D_REPACK_PIPE the loads of batch
+      // i + 1 are issued before the stores of batch i
+      const int ncg = (nchunk + 3) / 4, nbat = (kChP / 8) * ncg;
+      auto bat_ld = [&](float (&v)[32], int bi) {
+        const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ch = cg + k;
-              if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j * 4 + k]) : "r"(src + j * sstep + 128u * ch) : "memory");
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int ch = cg + k;
+            if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j * 4 + k]) : "r"(src + (c8 + j) * sstep + 128u * ch) : "memory");
+          }
+      };
+      auto bat_st = [&](const float (&v)[32], int bi) {
+        const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ch = cg + k;
-              if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + j * dstep + 128u * ch), "f"(v[j * 4 + k]) : "memory");
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int ch = cg + k;
+            if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (c8 + j) * dstep + 128u * ch), "f"(v[j * 4 + k]) : "memory");
+          }
+      };
+      if (B2D_REPACK_PIPE) {
+        float va[32], vb[32];
+        bat_ld(va, 0);
+        for (int bi = 0; bi < nbat; bi += 2) {
+          if (bi + 1 < nbat) bat_ld(vb, bi + 1);
+          bat_st(va, bi);
+          if (bi + 2 < nbat) bat_ld(va, bi + 2);
+          if (bi + 1 < nbat) bat_st(vb, bi + 1);
         }
-        src += 8 * sstep;
-        dst += 8 * dstep;
+      } else {
+        float va[32];
+        for (int bi = 0; bi < nbat; ++bi) {
+          bat_ld(va, bi);
+          bat_st(va, bi);
+        }
       }
       __syncwarp();
       if (kProducers > 1) asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");   // all producers done with the buffer
@@ -614,6 +802,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   }
   if (a.nostore) omask = 0u;
   const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)a.lane_stride * 4u;
+  // bulk stores need 16-byte aligned RoI slices: C * 49 * 4 bytes per RoI -> C % 4 == 0
+  const bool tile_out = FILL && nch == kCh && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out_g) & 15u) == 0 && !a.nostore;
+  int held = -1;        // pool tile a bulk store of this warp may still be reading
   const float4* recs = records_g + (size_t)f * a.items_cap * kRecVec;
   const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.bucket_start[(size_t)f * (nb + 2) + nb]);
 
@@ -712,6 +903,14 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
 
   while (pending < n_items) {
     pump();
+    // (`held` is warp-uniform; the reduction tells ptxas so - a branch it takes for divergent costs the
+    // consumers their [column + uniform row] tap addressing)
+    if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
+      // the bulk store issued by the previous item has (nearly always) read its tile by now
+      if (lane == 0) bulk_wait_read();
+      tile_release(s_tile_lock, held, lane);
+      held = -1;
+    }
     slot[lane] = rec_next;
     __syncwarp();
     const int nxt = claim();
@@ -723,7 +922,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int bucket = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
     float* o = out_g + ((size_t)r * C + c0) * bins + ph0 * kP;
-    if (!(code >> 16)) {
+    if (!((code >> 16) & 1)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       release(bucket);
       observe(min(bucket + nbk, nsteps));
@@ -736,15 +935,18 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
         release(nxt < n_items ? (int)nb_next : nsteps);
       };
       DBG_T0(t3);
-      switch (nph) {
-        case 1: run_item<1, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        case 2: run_item<2, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        case 3: run_item<3, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        case 4: run_item<4, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        case 5: run_item<5, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        case 6: run_item<6, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
-        default: run_item<7, S>(slot, nrows, lane_base, stage, lane, o, ooff, omask, early); break;
+#define B2D_RUN(N, NAR) \
+  run_item<N, S, NAR, FILL>(slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held, early)
+      if (B2D_NARROW && S == 2 && ((code >> 17) & 1)) {
+        if (nph <= 2) B2D_RUN(2, true);
+        else if (nph <= 4) B2D_RUN(4, true);
+        else B2D_RUN(7, true);
+      } else {
+        if (nph <= 2) B2D_RUN(2, false);
+        else if (nph <= 4) B2D_RUN(4, false);
+        else B2D_RUN(7, false);
       }
+#undef B2D_RUN
       DBG_ACC(3, t3);
 #ifdef B2D_ROWS_TIMING
       dbg_acc[4] += 0;
@@ -781,6 +983,10 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     for (int i = 0; i < 5; ++i) atomicAdd(&g_dbg[i], (unsigned long long)dbg_acc[i]);
 #endif
   release(nsteps);
+  if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {   // the last bulk store still reads shared memory
+    if (lane == 0) bulk_wait_read();
+    tile_release(s_tile_lock, held, lane);
+  }
   if (!FILL) {
     while (issued < nsteps) pump();
     asm volatile("cp.async.wait_all;" ::: "memory");
