@@ -19,26 +19,39 @@
 //
 // Data flow per CTA = (32-channel group, frame[, item split]).  The CTA streams the feature rows of
 // its 32 channels top to bottom through a ring of nblk blocks of St rows.  Lane c reads pixel
-// (row, x) of channel c at word  slot*row_words + c*lane_stride + x  with lane_stride = 1 (mod 32),
-// so the 32 lanes of a tap always hit 32 different banks.
+// (row, x) of channel c at word  slot*row_words + c*lane_stride + x  with an ODD lane_stride (W + 1 for
+// even W), so the 32 lanes of a tap always hit 32 different banks.
 //
-//   * TMA fill (W % 4 == 0): one producer warp.  Bulk TMA lands rows at 16-byte granularity, which
-//     would put channels c and c+8 on the same banks (and tiled-TMA box coordinates must be 16-byte
-//     aligned too: a per-channel element skew raises an illegal-instruction fault), so the rows are
-//     first pulled into a small dense staging buffer [32 ch][W] by 1-D bulk copies (one per channel
-//     row, several rows in flight, no registers, no issue slots) and the producer then repacks a
-//     staged row into its skewed ring slot with conflict-free LDS/STS - 2 wavefronts per 32
-//     elements, 3 % of the shared-memory budget.  (Register-staged LDG producers stall on address
-//     register reuse with only 6 scoreboards per warp; 4-byte cp.async from one warp sustains only
-//     ~8 copies in flight.)
+//   * TMA fill (plane size % 4 == 0): two producer warps.  TMA cannot write that layout: bulk and tiled
+//     copies land rows at 16-byte granularity (an odd pitch is impossible) and tiled box coordinates must
+//     be 16-byte aligned in the innermost dimension too (an element skew per channel or per box raises an
+//     illegal-instruction fault - measured twice).  So one tiled TMA per feature row (box = [32 planes][row],
+//     starting on the aligned element at or before the row) lands in a small dense staging buffer and the
+//     producers repack the staged row into its skewed ring slot with conflict-free LDS/STS - 2 wavefronts
+//     per 32 elements.  (Register-staged LDG producers stall on address register reuse with only 6
+//     scoreboards per warp; 4-byte cp.async from one warp sustains only ~8 copies in flight.)
 //   * cp.async fill (other shapes): every warp issues its share of a block as 4-byte LDGSTS whenever
 //     it looks (item boundaries and wait loops).
 //
-// Blocks are handed over with mbarriers only (full[b]: block landed, done[j]: every consumer warp
-// has left bucket j), there is no CTA-wide barrier after start-up: bucket k may touch blocks
-// k .. k+nbk-1 and the remaining nblk-nbk blocks are slack, so warps drift apart by that many
-// blocks.  A prep kernel turns the RoIs of a frame into self-contained item records sorted by first
-// row; warps claim items from a shared counter and prefetch the next record while they compute.
+// Blocks are handed over with mbarriers only (full[b]: block landed; TMA variant: consumers publish the
+// bucket they work in and the producers poll the minimum), there is no CTA-wide barrier after start-up:
+// bucket k may touch blocks k .. k+nbk-1 and the remaining nblk-nbk blocks are slack, so warps drift
+// apart by that many blocks.  A prep kernel turns the RoIs of a frame into self-contained item records
+// sorted by first row; warps claim items from a shared counter and prefetch the next record while they
+// compute.
+//
+// Output.  A whole-RoI item (nph = 7) of a full channel group is 6272 contiguous bytes of the output:
+// the warp try-locks one of kPool shared tiles, writes its 49 values per lane there and ONE bulk copy
+// (cp.async.bulk shared -> global) stores the slice - no LDS/STG round trip, half of all output bytes on
+// the bench workload.  Everything else is staged one bin-row [32 ch][7] at a time so that global stores
+// run along (c, pw).
+//
+// Two things ptxas must be told (each cost 10 % when missed): (1) every branch on a warp-uniform value
+// goes through a warp reduction (CREDUX -> uniform register); one branch it takes for divergent - the
+// producer/consumer split on threadIdx.x >> 5, a plain `held >= 0` - and every tap of the consumers
+// loses its [column + uniform row + imm] addressing to a per-tap IADD; (2) code size: the item code
+// is instantiated for 2, 4 and 7 accumulator rows only - one variant per nph, or per nph x {3-tap narrow
+// bins, 4-tap}, falls out of the instruction cache (4500+ instructions: 46 us/frame instead of 42).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
