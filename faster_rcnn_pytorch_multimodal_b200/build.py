@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2dglue.so")
-SOURCES = ["lib.cu", "proposal.cu", "nms.cu", "roi_align.cu", "roi_align_sweep.cu", "roi_align_rows.cu", "roi_align_bwd_rows.cu", "codecs.cu", "targets.cu", "uncertainty.cu", "detections.cu"]
+SOURCES = ["lib.cu", "proposal.cu", "nms.cu", "roi_align.cu", "roi_align_sweep.cu", "roi_align_rows.cu", "roi_align_bwd_rows.cu", "codecs.cu", "targets.cu", "uncertainty.cu", "detections.cu", "bev.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-cudart", "shared"]
 

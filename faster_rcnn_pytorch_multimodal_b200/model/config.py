@@ -24,6 +24,7 @@ __C = AttrDict()
 cfg = __C
 
 __C.NET_TYPE = 'lidar'                       # config.py:54
+__C.DB_NAME = ''                             # config.py:57; the CLIs set it (waymo / kitti / cadc / nuscenes)
 __C.USE_FPN = False                          # config.py:51
 __C.RNG_SEED = 3                             # config.py:346
 __C.POOLING_MODE = 'align'                   # config.py:364
@@ -84,6 +85,11 @@ __C.LIDAR.Y_RANGE = [-40, 40]                # config.py:398
 __C.LIDAR.Z_RANGE = [-3, 3]                  # config.py:399
 __C.LIDAR.VOXEL_LEN = 0.1                    # config.py:400
 __C.LIDAR.VOXEL_HEIGHT = 0.5                 # config.py:401
+__C.LIDAR.NUM_SLICES = 12                    # config.py:402
+__C.LIDAR.NUM_META_CHANNEL = 3               # config.py:403
+__C.LIDAR.NUM_CHANNEL = __C.LIDAR.NUM_SLICES + __C.LIDAR.NUM_META_CHANNEL   # config.py:404
+__C.LIDAR.MAX_PTS_PER_VOXEL = 32             # config.py:405
+__C.LIDAR.MAX_NUM_VOXEL = 25000              # config.py:406
 __C.LIDAR.ANCHORS = np.array([[4.73, 2.08, 1.77]])            # config.py:421
 __C.LIDAR.ANCHOR_SCALES = np.array([[1]])    # config.py:422
 __C.LIDAR.ANCHOR_ANGLES = np.array([0, np.pi / 2])            # config.py:423

@@ -236,6 +236,27 @@ int b2d_mc_class_uncertainty(int num_samples, int n, int num_classes, const floa
 int b2d_var_sort(int n, int cols, const float* var, int descending, float* key, int32_t* order, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * LiDAR BEV rasterisation for one frame of points.
+ * Replaces the CPU path of _get_lidar_blob()  roi_data_layer/minibatch.py:428-512:
+ *   filter_points() :232-235, z shift :454, spconv.utils.VoxelGeneratorV2.generate() :445-456
+ *   (spconv==1.0, req.txt:261: voxels in order of first appearance, capped at max_voxels; the
+ *   first max_pts_per_voxel points of a voxel in input order), the per-voxel max-height slices
+ *   :463-479, the density / tanh(mean intensity) / tanh(mean elongation) channels :481-509 (last
+ *   voxel of an (x, y) column wins, as the reference's fancy-index assignment does) and the
+ *   transpose :512.
+ *   points [num_points, num_feat] fp32 on the device (x, y, z, intensity[, elongation]);
+ *   ranges = cfg.LIDAR.{X,Y,Z}_RANGE, voxel_len = cfg.LIDAR.VOXEL_LEN / scale;
+ *   bev_map [ny, nx, nz + num_meta] fp32 (fully written, zeros included);
+ *   num_voxels (optional, device) = voxels kept.
+ * ---------------------------------------------------------------------------------- */
+size_t b2d_bev_workspace_bytes(int max_points, int nx, int ny, int nz);
+int b2d_bev_rasterize(int num_points, int num_feat, const float* points, float x_lo, float x_hi, float y_lo,
+                      float y_hi, float z_lo, float z_hi, float voxel_len, float voxel_height, int nx, int ny,
+                      int nz, int max_pts_per_voxel, int max_voxels, int num_meta, int elongation,
+                      float* bev_map, int32_t* num_voxels, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Final per-class detection filter, batched over frames and classes.
  * Replaces nms_hstack_torch() / filter_and_draw_prep()  utils/filter_predictions.py:45-130
  *          and the max-dets filter of the test loop       model/test.py:213-221.

@@ -299,5 +299,56 @@ def main():
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
 
+def gen_bev():
+    """tests/golden/bev.npz: the reference's own `_get_lidar_blob` (roi_data_layer/minibatch.py:237-512, test mode,
+    no augmentation) on synthetic sweeps.  `spconv` is not installable here: the voxeliser it calls is the
+    restatement in oracle/bev_oracle.py (see oracle/ref_import.load_minibatch), everything after it is the
+    reference's code.  Small ranges keep the fixture small; the caps are set low so that both bind."""
+    import tempfile
+    from . import bev_oracle as B
+    mb = ref_import.load_minibatch()
+    from model.config import cfg
+    out = {}
+    cases = {
+        # name: (x_range, y_range, max_pts, max_voxels, n_points, nfeat, db_name)
+        "caps": ((0, 8), (-4, 4), 4, 300, 6000, 5, "waymo"),
+        "roomy": ((0, 12), (-6, 6), 32, 25000, 20000, 5, "waymo"),
+        "kitti4": ((0, 8), (-4, 4), 32, 25000, 5000, 4, "kitti"),
+    }
+    saved = (cfg.LIDAR.X_RANGE, cfg.LIDAR.Y_RANGE, cfg.LIDAR.MAX_PTS_PER_VOXEL, cfg.LIDAR.MAX_NUM_VOXEL, cfg.DB_NAME,
+             cfg.LIDAR.NUM_META_CHANNEL, cfg.LIDAR.NUM_CHANNEL)
+    tmp = tempfile.mkdtemp()
+    for i, (name, (xr, yr, mp, mv, n, nf, db)) in enumerate(cases.items()):
+        cfg.LIDAR.X_RANGE, cfg.LIDAR.Y_RANGE = list(xr), list(yr)
+        cfg.LIDAR.MAX_PTS_PER_VOXEL, cfg.LIDAR.MAX_NUM_VOXEL = mp, mv
+        # the fork's KITTI sweeps carry no elongation: it runs them with the '.npy' loader and 2 meta channels
+        cfg.DB_NAME = "waymo" if db == "waymo" else "nuscenes"
+        cfg.LIDAR.NUM_META_CHANNEL = 3 if nf == 5 else 2
+        cfg.LIDAR.NUM_CHANNEL = cfg.LIDAR.NUM_SLICES + cfg.LIDAR.NUM_META_CHANNEL
+        lc = B.LidarCfg(x_range=xr, y_range=yr, max_pts_per_voxel=mp, max_num_voxel=mv, db_name=cfg.DB_NAME,
+                        num_meta_channel=cfg.LIDAR.NUM_META_CHANNEL)
+        pts = B.synth_point_cloud(SEED + i, n, lc, nfeat=nf)
+        f = os.path.join(tmp, f"{name}.npy")
+        np.save(f, pts)
+        ext = [xr[0], yr[0], cfg.LIDAR.Z_RANGE[0], xr[1], yr[1], cfg.LIDAR.Z_RANGE[1]]
+        infos, blob, _ = mb._get_lidar_blob([f], ext, 1.0, augment_en=False, mode="test")
+        out[f"{name}_points"] = pts
+        out[f"{name}_cfg"] = np.array([xr[0], xr[1], yr[0], yr[1], mp, mv, cfg.LIDAR.NUM_META_CHANNEL, db == "waymo"], dtype=np.float64)
+        out[f"{name}_info"] = np.asarray(infos[0], dtype=np.float64)
+        # sparse form of the [num_y, num_x, C] map: flat indices + values (the map is > 95 % zeros)
+        nz = np.flatnonzero(blob[0])
+        out[f"{name}_shape"] = np.asarray(blob[0].shape)
+        out[f"{name}_nz_idx"] = nz.astype(np.int64)
+        out[f"{name}_nz_val"] = blob[0].ravel()[nz]
+    (cfg.LIDAR.X_RANGE, cfg.LIDAR.Y_RANGE, cfg.LIDAR.MAX_PTS_PER_VOXEL, cfg.LIDAR.MAX_NUM_VOXEL, cfg.DB_NAME,
+     cfg.LIDAR.NUM_META_CHANNEL, cfg.LIDAR.NUM_CHANNEL) = saved
+    np.savez_compressed(os.path.join(OUT, "bev.npz"), **out)
+    print("bev.npz", os.path.getsize(os.path.join(OUT, "bev.npz")))
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    if "--only-bev" in sys.argv:
+        sys.exit(gen_bev())
+    rc = main()
+    gen_bev()
+    sys.exit(rc)

@@ -81,3 +81,49 @@ def load():
     ns.cfg, ns.bt, ns.ub, ns.ga, ns.sn, ns.g3 = cfg, bt, ub, ga, sn, g3
     ns.pl, ns.ptl, ns.atl, ns.prt, ns.lu, ns.tp = pl, ptl, atl, prt, lu, tp
     return ns
+
+
+def load_minibatch():
+    """Import the reference's ``roi_data_layer/minibatch.py`` (for `_get_lidar_blob`).
+
+    Its module-level imports pull in packages that are not installed here and are not touched by the
+    BEV rasterisation itself (cv2, imgaug, pyntcloud, PIL, the dataset classes, the calibration helpers):
+    they are stubbed with empty modules.  ``spconv`` (pinned 1.0, ``req.txt:261``, not installable) is
+    stubbed with the restatement in ``oracle/bev_oracle.py`` - the ONE piece of arithmetic on this path
+    that therefore stays unpinned."""
+    if not available():
+        raise RuntimeError("/root/reference is not present (expected on the GPU box)")
+    _install_stubs()
+    if REF_LIB not in sys.path:
+        sys.path.insert(0, REF_LIB)
+    from . import bev_oracle
+
+    def stub(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    for name in ("imgaug", "imgaug.augmenters", "pyntcloud", "PIL", "PIL.Image", "PIL.ImageDraw", "PIL.ImageEnhance",
+                 "scipy.ndimage.filters", "datasets.waymo_lidb", "utils.kitti_utils", "utils.CADC_utils"):
+        try:
+            __import__(name)
+        except Exception:
+            stub(name)
+    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+    for n in ("Image", "ImageDraw", "ImageEnhance"):
+        setattr(sys.modules["PIL"], n, sys.modules["PIL." + n])
+    if not hasattr(sys.modules["pyntcloud"], "PyntCloud"):
+        sys.modules["pyntcloud"].PyntCloud = object
+    if not hasattr(sys.modules["scipy.ndimage.filters"], "gaussian_filter"):
+        sys.modules["scipy.ndimage.filters"].gaussian_filter = None
+    if not hasattr(sys.modules["datasets.waymo_lidb"], "waymo_lidb"):
+        sys.modules["datasets.waymo_lidb"].waymo_lidb = object
+    if not hasattr(sys.modules["utils.kitti_utils"], "Calibration"):
+        sys.modules["utils.kitti_utils"].Calibration = object
+    sp = stub("spconv")
+    sp.utils = stub("spconv.utils", VoxelGeneratorV2=bev_oracle.VoxelGeneratorV2)
+    import roi_data_layer.minibatch as mb
+    return mb
