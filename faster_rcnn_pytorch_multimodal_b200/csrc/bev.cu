@@ -18,7 +18,8 @@
 //   fill    every point drops its index into its bucket -> each voxel owns the (unordered) list of its
 //           point indices, contiguous in memory;
 //   first   one warp per voxel: smallest index = the voxel's first appearance, flagged in a per-point
-//           bitmap; an exclusive scan of the bitmap is the voxel's rank in the reference's order;
+//           bitmap; the number of set bits before it (one-CTA popcount scan over the bitmap words) is the
+//           voxel's rank in the reference's order;
 //   voxel   one warp per voxel: rank < max_voxels keeps it; if it has more than max_pts points the
 //           ones with fewer than max_pts smaller indices are the first max_pts in input order
 //           (rank-by-counting inside the bucket, voxels that dense are rare); max z, count and the
@@ -97,12 +98,32 @@ __global__ void __launch_bounds__(256) key_kernel(int n, const float* __restrict
   w.slot[i] = k >= 0 ? atomicAdd(&w.cnt[k], 1) : -1;
 }
 
+// warp-aggregated: one atomic per warp on each of the two cursors (100 k voxels on two addresses
+// serialise otherwise: 79 us -> a few us)
 __global__ void __launch_bounds__(256) alloc_kernel(int n, Ws w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || w.slot[i] != 0) return;
-  const int k = w.key[i];
-  w.base[k] = atomicAdd(&w.counters[0], w.cnt[k]);
-  w.vkey[atomicAdd(&w.counters[1], 1)] = k;
+  const int lane = threadIdx.x & 31;
+  const bool owner = i < n && w.slot[i] == 0;
+  const int k = owner ? w.key[i] : 0;
+  const int c = owner ? w.cnt[k] : 0;
+  const unsigned m = __ballot_sync(0xffffffffu, owner);
+  if (!m) return;
+  int inc = c;                                   // inclusive prefix of the bucket sizes over the warp
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  int b0 = 0, v0 = 0;
+  if (lane == 31) {
+    b0 = atomicAdd(&w.counters[0], inc);
+    v0 = atomicAdd(&w.counters[1], __popc(m));
+  }
+  b0 = __shfl_sync(0xffffffffu, b0, 31);
+  v0 = __shfl_sync(0xffffffffu, v0, 31);
+  if (owner) {
+    w.base[k] = b0 + inc - c;
+    w.vkey[v0 + __popc(m & ((1u << lane) - 1u))] = k;
+  }
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(int n, Ws w) {
@@ -124,19 +145,22 @@ __global__ void __launch_bounds__(256) first_kernel(Ws w) {
     m = (int)__reduce_min_sync(0xffffffffu, (unsigned)m);
     if (lane == 0) {
       w.vfirst[v] = m;
-      w.flag[m] = 1;
+      atomicOr(reinterpret_cast<unsigned*>(&w.flag[m >> 5]), 1u << (m & 31));
     }
   }
 }
 
-// exclusive scan of flag[0, n) by one CTA (n is a few hundred thousand)
+// flag is a bitmap over the points (bit i: point i is the first of its voxel); rank[wd] = number of set bits
+// before word wd, so the rank of the voxel that starts at point i is rank[i >> 5] + popc(bits below i).
+// One CTA: a few thousand words.
 __global__ void __launch_bounds__(1024) scan_kernel(int n, Ws w) {
   __shared__ int warp_sum[32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  const int nwords = (n + 31) / 32;
+  const int per = (nwords + 1023) / 1024;
+  const int lo = min(nwords, tid * per), hi = min(nwords, lo + per);
   int s = 0;
-  for (int i = lo; i < hi; ++i) s += w.flag[i];
+  for (int i = lo; i < hi; ++i) s += __popc((unsigned)w.flag[i]);
   int inc = s;
   for (int d = 1; d < 32; d <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(int n, Ws w) {
   int run = inc - s + (wid ? warp_sum[wid - 1] : 0);
   for (int i = lo; i < hi; ++i) {
     w.rank[i] = run;
-    run += w.flag[i];
+    run += __popc((unsigned)w.flag[i]);
   }
 }
 
@@ -168,7 +192,8 @@ __global__ void __launch_bounds__(256) voxel_kernel(const float* __restrict__ pt
   const int C = g.nz + g.n_meta;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_voxels_out) *num_voxels_out = min(nvox, g.max_voxels);
   for (int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < nvox; v += nw) {
-    const int vr = w.rank[w.vfirst[v]];
+    const int f0 = w.vfirst[v];
+    const int vr = w.rank[f0 >> 5] + __popc((unsigned)w.flag[f0 >> 5] & ((1u << (f0 & 31)) - 1u));
     if (vr >= g.max_voxels) {                  // created past the cap: the reference never saw this voxel
       if (lane == 0) w.vrank[v] = -1;
       continue;
