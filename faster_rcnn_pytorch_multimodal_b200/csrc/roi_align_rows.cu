@@ -77,6 +77,9 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #ifndef B2D_ROW_UNROLL
 #define B2D_ROW_UNROLL 1
 #endif
+#ifndef B2D_FFMA2
+#define B2D_FFMA2 1
+#endif
 #ifndef B2D_TAP_PIPE
 #define B2D_TAP_PIPE 0
 #endif
@@ -323,22 +326,41 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
         }
       }
       if (!narrow) {
+        int xo[2 * kP];
+        float hx[2 * kP], lx[2 * kP];
         for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
-          int xo = 0;
-          float hx = 0.0f, lx = 0.0f;
+          xo[k] = 0;
+          hx[k] = lx[k] = 0.0f;
           if (k < kP * S) {
             const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
             if (t.ok) {
-              xo = t.lo * 4;
-              hx = t.wlo;
-              lx = t.whi;
+              xo[k] = t.lo * 4;
+              hx[k] = t.wlo;
+              lx[k] = t.whi;
             }
           }
-          xw[3 * k] = __int_as_float(xo);
-          xw[3 * k + 1] = hx;
-          xw[3 * k + 2] = lx;
         }
-        xw[42] = xw[43] = 0.0f;
+        if (S == 2 && B2D_FFMA2) {
+          // pair layout for the packed contraction: 14 offsets, then per bin pair (2j, 2j+1) the weights of
+          // tap a / b of the first sample and c / d of the second as aligned register pairs, then bin 6
+          for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
+          xw[14] = xw[15] = 0.0f;
+          for (int j = 0; j < 3; ++j) {
+            float* q = xw + 16 + 8 * j;
+            q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
+            q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
+            q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
+            q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
+          }
+          xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
+        } else {
+          for (int k = 0; k < 2 * kP; ++k) {
+            xw[3 * k] = __int_as_float(xo[k]);
+            xw[3 * k + 1] = hx[k];
+            xw[3 * k + 2] = lx[k];
+          }
+          xw[42] = xw[43] = 0.0f;
+        }
       }
       // distinct feature rows of the item and their weights per bin-row
       int nrows = 0;
@@ -479,6 +501,20 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       mx[k] = t.z;
       lx[k] = t.w;
     }
+  } else if (B2D_FFMA2 && S == 2) {
+    // offsets only; the weights are read as pairs below
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4 t = slot[1 + v];
+      xa[4 * v] = lane_base + (uint32_t)__float_as_int(t.x);
+      xa[4 * v + 1] = lane_base + (uint32_t)__float_as_int(t.y);
+      if (v < 3) {
+        xa[4 * v + 2] = lane_base + (uint32_t)__float_as_int(t.z);
+        xa[4 * v + 3] = lane_base + (uint32_t)__float_as_int(t.w);
+      }
+    }
+    const float4 l = slot[1 + 10];
+    hx[12] = l.x, lx[12] = l.y, hx[13] = l.z, lx[13] = l.w;
   } else {
     float q[4 * kXVec];
 #pragma unroll
@@ -496,11 +532,27 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       lx[k] = q[3 * k + 2];
     }
   }
-  float acc[NPH][kP];
+  // accumulators as register pairs (pw = 2j, 2j+1 in acc2[p][j]; pw = 6 in acc2[p][3].x): the contraction
+  // below runs on packed fp32 FMAs (FFMA2, sm_100), which halves its issue slots
+  float2 acc2[NPH][4];
 #pragma unroll
   for (int p = 0; p < NPH; ++p)
 #pragma unroll
-    for (int pw = 0; pw < kP; ++pw) acc[p][pw] = 0.0f;
+    for (int j = 0; j < 4; ++j) acc2[p][j] = make_float2(0.0f, 0.0f);
+#define B2D_ACC(p, pw) (((pw) & 1) ? acc2[p][(pw) >> 1].y : acc2[p][(pw) >> 1].x)
+  constexpr bool PACK = B2D_FFMA2 && S == 2 && !NARROW;
+  // x weights of the bin pairs (0,1), (2,3), (4,5): tap a, b of the first sample, c, d of the second
+  float2 wa[PACK ? 3 : 1], wb[PACK ? 3 : 1], wc[PACK ? 3 : 1], wd[PACK ? 3 : 1];
+  if (PACK) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 u = slot[1 + 4 + 2 * j], v = slot[1 + 5 + 2 * j];
+      wa[j] = make_float2(u.x, u.y);
+      wb[j] = make_float2(u.z, u.w);
+      wc[j] = make_float2(v.x, v.y);
+      wd[j] = make_float2(v.z, v.w);
+    }
+  }
 
   constexpr int NT = NARROW ? 3 * kP : 2 * S * kP;      // taps per feature row
   auto load_row = [&](float (&t)[NT], uint32_t ro) {
@@ -534,6 +586,29 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
         wy[6] = f1.w;
       }
     }
+    if (PACK) {
+      // same operations per element as the scalar path (FMUL, then three FMAs; one FMA per accumulator)
+      float2 T2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T2[j] = __fmul2_rn(wa[j], make_float2(t[8 * j], t[8 * j + 4]));
+        T2[j] = __ffma2_rn(wb[j], make_float2(t[8 * j + 1], t[8 * j + 5]), T2[j]);
+        T2[j] = __ffma2_rn(wc[j], make_float2(t[8 * j + 2], t[8 * j + 6]), T2[j]);
+        T2[j] = __ffma2_rn(wd[j], make_float2(t[8 * j + 3], t[8 * j + 7]), T2[j]);
+      }
+      float t6 = hx[12] * t[24];
+      t6 = fmaf(lx[12], t[25], t6);
+      t6 = fmaf(hx[13], t[26], t6);
+      t6 = fmaf(lx[13], t[27], t6);
+#pragma unroll
+      for (int p = 0; p < NPH; ++p) {
+        const float2 w2 = make_float2(wy[p], wy[p]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc2[p][j] = __ffma2_rn(w2, T2[j], acc2[p][j]);
+        acc2[p][3].x = fmaf(wy[p], t6, acc2[p][3].x);
+      }
+      return;
+    }
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
       float v;
@@ -551,7 +626,7 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
         v = fmaf(lx[pw], t[2 * pw + 1], v);
       }
 #pragma unroll
-      for (int p = 0; p < NPH; ++p) acc[p][pw] = fmaf(wy[p], v, acc[p][pw]);
+      for (int p = 0; p < NPH; ++p) B2D_ACC(p, pw) = fmaf(wy[p], v, B2D_ACC(p, pw));
     }
   };
   // The row offset is the same in every lane; the reduction tells ptxas so (CREDUX -> uniform register),
@@ -604,7 +679,7 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 #pragma unroll
         for (int p = 0; p < NPH; ++p)
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) tile[lane * (kP * kP) + p * kP + pw] = acc[p][pw];   // 49 words per lane: odd pitch
+          for (int pw = 0; pw < kP; ++pw) tile[lane * (kP * kP) + p * kP + pw] = B2D_ACC(p, pw);   // 49 words per lane: odd pitch
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
         __syncwarp();
         if (lane == 0) bulk_s2g(o, smem_u32(tile), (uint32_t)kTileWords * 4u);
@@ -621,13 +696,14 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
     float* tile = stage + (B2D_OUT_TILES > 1 ? (p & 1) * (kCh * kP) : 0);
     if (B2D_OUT_TILES == 1 && p > 0) __syncwarp();
 #pragma unroll
-    for (int pw = 0; pw < kP; ++pw) tile[lane * kP + pw] = acc[p][pw];
+    for (int pw = 0; pw < kP; ++pw) tile[lane * kP + pw] = B2D_ACC(p, pw);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kP; ++j)
       if (omask & (1u << j)) o[p * kP + ooff[j]] = tile[lane + 32 * j];
   }
   __syncwarp();
+#undef B2D_ACC
 }
 
 struct KArgs {
