@@ -34,6 +34,7 @@ PROTOTYPES = {
     "b2d_roi_align_workspace_bytes": (SZ, [I, I, I, I, I, I]),
     "b2d_roi_align_forward": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, _f, _v, SZ, _v]),
     "b2d_roi_align_backward": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, I, _f, _v, SZ, _v]),
+    "b2d_roi_align_forward_levels": (I, [I, I, I, _v, _i, _i, _v, _f, _i, I, I, I, I, I, _f, _v]),
     "b2d_fpn_level_map": (I, [I, _f, I, I, F32, I, F32, _i, _v]),
     "b2d_bbox_overlaps": (I, [I, I, _f, I, _f, I, _f, _v]),
     "b2d_bbox_transform": (I, [I, _f, I, _f, I, _f, _v]),

@@ -19,6 +19,8 @@
 // one thread per channel.  A thread is the only writer of its channel plane, RoIs are
 // visited in index order, so accumulation is deterministic with no atomics at all; each
 // grad_feat element is written to HBM exactly once.
+#include <stdlib.h>
+
 #include "roi_common.cuh"
 
 namespace b2d {
@@ -164,6 +166,54 @@ roi_align_fwd_gather_kernel(const float* __restrict__ feat, RoiList L, int F, in
   }
 }
 
+// Multi-level form of the gather kernel (MultiScaleRoIAlign on one frame's RoIs): the level of every RoI picks
+// the feature map, its size and its scale, so a whole FPN crop is ONE launch with no per-level index lists.
+constexpr int kMaxLevels = 8;
+struct LevelSet {
+  const float* feat[kMaxLevels];
+  int H[kMaxLevels], W[kMaxLevels];
+  float scale[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(256)
+roi_align_fwd_gather_levels_kernel(LevelSet S, int num_levels, const float* __restrict__ rois,
+                                   const int32_t* __restrict__ levels, int R, int F, int C, int PH, int PW,
+                                   int sampling_ratio, int aligned, float* __restrict__ out) {
+  const int bins = PH * PW;
+  const long long total = (long long)R * C * bins;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int bin = (int)(idx % bins);
+    const int c = (int)((idx / bins) % C);
+    const int r = (int)(idx / ((long long)bins * C));
+    const float* roi = rois + (size_t)r * 5;
+    const int f = (int)roi[0];
+    const int lv = levels[r];
+    float val = 0.0f;
+    if (f >= 0 && f < F && lv >= 0 && lv < num_levels) {
+      const int H = S.H[lv], W = S.W[lv];
+      const float* p = S.feat[lv] + ((size_t)f * C + c) * H * W;
+      const int ph = bin / PW, pw = bin - ph * PW;
+      const RoiGeom g = roi_geometry(roi, S.scale[lv], PH, PW, sampling_ratio, aligned != 0);
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+        for (int ix = 0; ix < g.grid_w; ++ix) {
+          const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
+          if (!(ty.ok && tx.ok)) continue;
+          const float w1 = fmul(ty.wlo, tx.wlo), w2 = fmul(ty.wlo, tx.whi);
+          const float w3 = fmul(ty.whi, tx.wlo), w4 = fmul(ty.whi, tx.whi);
+          const float v = fadd(fadd(fadd(fmul(w1, __ldg(p + ty.lo * W + tx.lo)), fmul(w2, __ldg(p + ty.lo * W + tx.hi))),
+                                    fmul(w3, __ldg(p + ty.hi * W + tx.lo))),
+                               fmul(w4, __ldg(p + ty.hi * W + tx.hi)));
+          val = fadd(val, v);
+        }
+      }
+      val = fdiv(val, g.count);
+    }
+    out[idx] = val;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Backward.  Shared accumulators acc[(y - y0) * W + x][33], thread = channel.
 constexpr int kBwdCh = 32;
@@ -306,14 +356,20 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
   if (L.n <= 0) return B2D_OK;
   if (!rois) return B2D_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
-  // production path: channel-on-lanes sweep kernel (roi_align_sweep.cu); needs the workspace
+  const long long total = (long long)L.n * C * PH * PW;
+  // Few RoIs on few channel groups (one FPN level of one frame: ~75 RoIs x 256 channels): the streaming
+  // kernels would run 8-32 CTAs and pull the whole level through shared memory for a handful of RoIs
+  // (p3 160x240: 325 us); one thread per output straight from L2 takes 20-45 us.  The gather kernel costs
+  // ~30 ps per output, the streaming kernels ~2.5 ps at full occupancy.
+  // (B2D_ROI_NO_GATHER: test knob, keeps small test shapes on the streaming kernels)
+  const bool sparse = total <= (1LL << 22) && (long long)ceil_div(C, 32) * F < kNumSMs / 2 && !getenv("B2D_ROI_NO_GATHER");
   // production path: 7x7 "rows" kernel (roi_align_rows.cu), then the generic sweep kernel; both need the workspace
-  if (C >= 16) {
+  if (C >= 16 && !sparse) {
     const int rc = roi_align_forward_rows(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
                                           workspace, workspace_bytes, st);
     if (rc != B2D_ERR_UNSUPPORTED) return rc;
   }
-  if (C >= 16) {
+  if (C >= 16 && !sparse) {
     const int rc = roi_align_forward_sweep(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
                                            workspace, workspace_bytes, st);
     if (rc != B2D_ERR_UNSUPPORTED) return rc;
@@ -322,7 +378,7 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
   int cpb = (int)(fwd_smem_budget() / plane);
   if (cpb > 8) cpb = 8;
   if (cpb > C) cpb = C;
-  if (cpb >= 1) {
+  if (cpb >= 1 && !sparse) {
     const int use_bulk = ((H * W) % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15u) == 0);
     switch (cpb) {
       case 1: return launch_fwd_planes<1>(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, use_bulk, out, st);
@@ -335,11 +391,36 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
       default: return launch_fwd_planes<8>(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, use_bulk, out, st);
     }
   }
-  const long long total = (long long)L.n * C * PH * PW;
   long long blocks = (total + 255) / 256;
   if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
   roi_align_fwd_gather_kernel<<<(int)blocks, 256, 0, st>>>(feat, L, F, C, H, W, PH, PW, spatial_scale, sampling_ratio,
                                                            aligned, out);
+  B2D_LAUNCHED();
+  return B2D_OK;
+}
+
+extern "C" int b2d_roi_align_forward_levels(int num_levels, int F, int C, const float* const* feats, const int32_t* heights,
+                                            const int32_t* widths, const float* scales, const float* rois,
+                                            const int32_t* levels, int num_rois, int PH, int PW, int sampling_ratio,
+                                            int aligned, float* out, void* stream) {
+  if (num_levels <= 0 || num_levels > kMaxLevels || F <= 0 || C <= 0 || PH <= 0 || PW <= 0 || !feats || !heights ||
+      !widths || !scales || !out)
+    return B2D_ERR_INVALID_ARG;
+  if (num_rois <= 0) return B2D_OK;
+  if (!rois || !levels) return B2D_ERR_INVALID_ARG;
+  LevelSet S{};
+  for (int i = 0; i < num_levels; ++i) {
+    if (!feats[i] || heights[i] <= 0 || widths[i] <= 0) return B2D_ERR_INVALID_ARG;
+    S.feat[i] = feats[i];
+    S.H[i] = heights[i];
+    S.W[i] = widths[i];
+    S.scale[i] = scales[i];
+  }
+  const long long total = (long long)num_rois * C * PH * PW;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
+  roi_align_fwd_gather_levels_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(S, num_levels, rois, levels, num_rois, F, C,
+                                                                              PH, PW, sampling_ratio, aligned, out);
   B2D_LAUNCHED();
   return B2D_OK;
 }

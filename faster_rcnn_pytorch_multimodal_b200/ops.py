@@ -230,8 +230,28 @@ class RoIAlign(torch.nn.Module):
         return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
 
 
+def roi_align_forward_levels(feats, scales, rois, levels_i32, out_hw, sampling_ratio, aligned=False):
+    """One-launch multi-level RoIAlign forward (small calls): feats = per-level [F,C,H,W] maps, levels_i32 [R]."""
+    import ctypes as C
+    require_cuda(rois, levels_i32, *feats)
+    feats = [f32c(f) for f in feats]
+    rois = f32c(rois)
+    n = len(feats)
+    Fr, Cc = feats[0].shape[:2]
+    R = rois.shape[0]
+    out = torch.empty(R, Cc, out_hw[0], out_hw[1], device=rois.device)
+    fp = (C.c_void_p * n)(*[f.data_ptr() for f in feats])
+    hh = (C.c_int32 * n)(*[f.shape[2] for f in feats])
+    ww = (C.c_int32 * n)(*[f.shape[3] for f in feats])
+    sc = (C.c_float * n)(*[float(s) for s in scales])
+    check(lib().b2d_roi_align_forward_levels(n, Fr, Cc, fp, hh, ww, sc, ptr(rois), ptr(levels_i32), R, out_hw[0], out_hw[1],
+                                             int(sampling_ratio), int(bool(aligned)), ptr(out), stream_ptr(rois.device)),
+          "b2d_roi_align_forward_levels")
+    return out
+
+
 def fpn_level_map(boxes: torch.Tensor, k_min: int, k_max: int, canonical_scale: float = 224,
-                  canonical_level: int = 4, eps: float = 1e-6) -> torch.Tensor:
+                  canonical_level: int = 4, eps: float = 1e-6, as_int32: bool = False) -> torch.Tensor:
     """LevelMapper.__call__ (utils/torchpoolers.py:39-51) on one concatenated [R,4] tensor -> int64 [R]."""
     require_cuda(boxes)
     boxes = f32c(boxes)
@@ -239,7 +259,7 @@ def fpn_level_map(boxes: torch.Tensor, k_min: int, k_max: int, canonical_scale: 
     check(lib().b2d_fpn_level_map(boxes.shape[0], ptr(boxes), int(k_min), int(k_max), float(canonical_scale),
                                   int(canonical_level), float(eps), ptr(out), stream_ptr(boxes.device)),
           "b2d_fpn_level_map")
-    return out.long()
+    return out if as_int32 else out.long()
 
 
 # ------------------------------------------------------------------------------------------

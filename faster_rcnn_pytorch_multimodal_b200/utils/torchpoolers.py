@@ -19,9 +19,9 @@ class LevelMapper(object):
         self.k_min, self.k_max = k_min, k_max
         self.s0, self.lvl0, self.eps = canonical_scale, canonical_level, eps
 
-    def __call__(self, boxlists):
+    def __call__(self, boxlists, as_int32=False):
         return ops.fpn_level_map(torch.cat(list(boxlists), dim=0), self.k_min, self.k_max, self.s0, self.lvl0,
-                                 self.eps)
+                                 self.eps, as_int32=as_int32)
 
 
 def initLevelMapper(k_min, k_max, canonical_scale=224, canonical_level=4, eps=1e-6):
@@ -68,8 +68,11 @@ class MultiScaleRoIAlign(nn.Module):
             self.setup_scales(feats, image_shapes)
         if len(feats) == 1:
             return ops.roi_align(feats[0], rois, self.output_size, self.scales[0], self.sampling_ratio)
-        levels = self.map_levels(boxes)
+        levels = self.map_levels(boxes, as_int32=True)
         return _MultiLevelFn.apply(rois, levels, self.output_size, tuple(self.scales), self.sampling_ratio, *feats)
+
+
+_FUSED_MAX_OUTPUTS = 1 << 23     # above this the per-level streaming kernels win (ops.roi_align dispatch)
 
 
 class _MultiLevelFn(torch.autograd.Function):
@@ -77,6 +80,13 @@ class _MultiLevelFn(torch.autograd.Function):
     def forward(ctx, rois, levels, out_hw, scales, sampling_ratio, *feats):
         rois_c = ops.f32c(rois)
         R, C = rois_c.shape[0], feats[0].shape[1]
+        ctx.meta = (out_hw, scales, sampling_ratio, [tuple(f.shape) for f in feats])
+        if R * C * out_hw[0] * out_hw[1] <= _FUSED_MAX_OUTPUTS and len(feats) <= 8:
+            # one frame's worth of RoIs: one launch for all levels, no index lists, no host sync
+            ctx.save_for_backward(rois_c, levels)
+            ctx.fused = True
+            return ops.roi_align_forward_levels(feats, scales, rois_c, levels, out_hw, sampling_ratio)
+        ctx.fused = False
         out = torch.zeros((R, C) + tuple(out_hw), device=feats[0].device)
         id_lists = []
         for lvl, (f, s) in enumerate(zip(feats, scales)):
@@ -84,13 +94,16 @@ class _MultiLevelFn(torch.autograd.Function):
             id_lists.append(ids)
             ops._roi_align_forward(ops.f32c(f), rois_c, out_hw, s, sampling_ratio, False, roi_ids=ids, out=out)
         ctx.save_for_backward(rois_c, *id_lists)
-        ctx.meta = (out_hw, scales, sampling_ratio, [tuple(f.shape) for f in feats])
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        rois_c, *id_lists = ctx.saved_tensors
         out_hw, scales, sr, shapes = ctx.meta
+        if ctx.fused:
+            rois_c, levels = ctx.saved_tensors
+            id_lists = [(levels == lvl).nonzero().view(-1).to(torch.int32).contiguous() for lvl in range(len(shapes))]
+        else:
+            rois_c, *id_lists = ctx.saved_tensors
         g = ops.f32c(grad_out)
         grads = [ops._roi_align_backward(g, rois_c, shp, out_hw, s, sr, False, roi_ids=ids)
                  for shp, s, ids in zip(shapes, scales, id_lists)]

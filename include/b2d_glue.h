@@ -139,6 +139,18 @@ int b2d_roi_align_backward(int num_frames, int channels, int height, int width,
                            int accumulate, float* grad_feat, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* MultiScaleRoIAlign.forward  utils/torchpoolers.py:137-200 for small calls (one frame's RoIs) in ONE launch:
+ * replaces the per-level nonzero / index_select / roi_align / scatter loop :187-199.
+ *   feats[num_levels] device pointers to [F, C, heights[l], widths[l]] fp32 maps (HOST arrays of num_levels
+ *   entries, read during the call), scales[l] = spatial scale of level l, rois [R,5], levels [R] int32
+ *   (b2d_fpn_level_map) -> out [R, C, pooled_h, pooled_w], every row written.  One thread per output element
+ *   straight from L2: meant for R * C * pooled_h * pooled_w up to a few million; larger batches run
+ *   b2d_roi_align_forward once per level with an index list. */
+int b2d_roi_align_forward_levels(int num_levels, int num_frames, int channels, const float* const* feats,
+                                 const int32_t* heights, const int32_t* widths, const float* scales,
+                                 const float* rois, const int32_t* levels, int num_rois, int pooled_h, int pooled_w,
+                                 int sampling_ratio, int aligned, float* out, void* stream);
+
 /* FPN level assignment, LevelMapper.__call__  utils/torchpoolers.py:39-51.
  *   boxes [R,4] -> levels [R] int32 in [0, k_max-k_min]. */
 int b2d_fpn_level_map(int num_rois, const float* boxes, int k_min, int k_max, float canonical_scale,

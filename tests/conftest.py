@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "sparse_path: RoIAlign test that runs with the production dispatch (gather kernel for small calls)")
 
 
 def load_golden(name):

@@ -20,6 +20,15 @@ def dev():
     return torch.device("cuda", 0)
 
 
+@pytest.fixture(autouse=True)
+def _streaming_roi_kernels(request, monkeypatch):
+    """Small RoIAlign calls (one FPN level of one frame) are routed to the gather kernel; the test shapes are that
+    small too, so the suite pins them to the streaming kernels (rows / sweep / planes) they are meant to cover.
+    Tests marked `sparse_path` run with the production dispatch."""
+    if "sparse_path" not in request.keywords:
+        monkeypatch.setenv("B2D_ROI_NO_GATHER", "1")
+
+
 def T(a, d=None):
     return torch.from_numpy(np.ascontiguousarray(a)).to(d or dev())
 
@@ -252,6 +261,15 @@ def test_proposal_layer_image_configs(name, Hf, Wf, W, H, key, pre, post):
     _run_proposal_vs_oracle(prob, deltas, info, anchors, None, A, key, pre, post)
 
 
+def test_proposal_layer_fpn_p2_scale():
+    """configs[3]: RPN on FPN level p2 of a Waymo frame, 320 x 480 x 25 = 3.84 M anchors at stride 4."""
+    Hf, Wf, A = 320, 480, 25
+    prob, deltas = synth_rpn(13, Hf, Wf, A)
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 4, FORK_SCALES, FORK_RATIOS, 1.0)[0])
+    info = np.array([0, 1920, 0, 1280, 0, 0, 1.0], dtype=np.float32)
+    _run_proposal_vs_oracle(prob, deltas, info, anchors, None, A, "TEST", 6000, 300)
+
+
 def test_proposal_layer_lidar_config():
     Hf, Wf, A = 50, 44, 2
     prob, deltas = synth_rpn(12, Hf, Wf, A)
@@ -363,6 +381,19 @@ def test_roi_align_forward_backward_vs_torchvision(C, H, W, R, sr):
     close(f_gpu.grad, f_ref.grad, atol=1e-5 * float(f_ref.grad.abs().max()))
 
 
+@pytest.mark.sparse_path
+@pytest.mark.parametrize("C,H,W,R", [(256, 160, 240, 75), (256, 320, 480, 120), (64, 24, 78, 300)])
+def test_roi_align_sparse_dispatch_vs_torchvision(C, H, W, R):
+    """Production dispatch for one FPN level of one frame (few RoIs, few channel groups): gather kernel."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    feat = torch.randn(1, C, H, W, generator=g)
+    rois = _random_rois(H + R, R, W * 4, H * 4)
+    want = O.roi_align(feat, rois, (7, 7), 0.25, 2, False)
+    got = ops.roi_align(feat.to(dev()), rois.to(dev()), (7, 7), 0.25, 2, False)
+    close(got, want, atol=1e-5)
+
+
 def _stress_rois(seed, F, M, W, H):
     """Proposal-like mix incl. the awkward cases: tiny, full-frame (taller than the ring window),
     zero-area, partly and wholly outside the frame."""
@@ -468,10 +499,17 @@ def test_roi_align_backward_is_deterministic():
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
 
 
-def test_fpn_level_map_and_multiscale(golden):
+@pytest.mark.sparse_path
+@pytest.mark.parametrize("fused", [True, False])
+def test_fpn_level_map_and_multiscale(golden, fused, monkeypatch):
+    """fused: one launch for all levels (small calls); not fused: one streaming launch per level with index lists."""
     from collections import OrderedDict
     from faster_rcnn_pytorch_multimodal_b200 import ops
+    from faster_rcnn_pytorch_multimodal_b200.utils import torchpoolers
     from faster_rcnn_pytorch_multimodal_b200.utils.torchpoolers import MultiScaleRoIAlign
+    if not fused:
+        monkeypatch.setattr(torchpoolers, "_FUSED_MAX_OUTPUTS", 0)
+        monkeypatch.setenv("B2D_ROI_NO_GATHER", "1")
     g = golden("thirdparty")
     fb = T(g["fpn_boxes"])
     assert torch.equal(ops.fpn_level_map(fb, 2, 5).cpu(), torch.from_numpy(g["fpn_levels"]))
