@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(256) anchor_label_kernel(int N, int max_gt, co
   }
 }
 
-// ordered compaction of the fg / bg anchor lists, one CTA per frame
+// ordered compaction of the fg / bg anchor lists, one CTA per frame; every thread owns 16 consecutive anchors
+// per round (16 384 per round: 15 rounds at Waymo size instead of 235 rounds of 1024 with 4 barriers each)
 __global__ void __launch_bounds__(1024) anchor_lists_kernel(int N, AnchorWs w, int32_t* __restrict__ counts) {
+  constexpr int kPer = 16;
   __shared__ int s_warp[3][32];
   __shared__ int s_base[3];
   __shared__ int s_tot[3];
@@ -158,32 +160,48 @@ __global__ void __launch_bounds__(1024) anchor_lists_kernel(int N, AnchorWs w, i
   if (threadIdx.x < 3) s_base[threadIdx.x] = 0;
   __syncthreads();
   const int8_t* label = w.label + (size_t)f * N;
-  for (int base = 0; base < N; base += 1024) {
-    const int n = base + threadIdx.x;
-    const int8_t lab = n < N ? label[n] : (int8_t)-2;
-    const bool flag[3] = {lab != -2, lab == 1, lab == 0};
-    int rank[3];
+  for (int base = 0; base < N; base += 1024 * kPer) {
+    const int n0 = base + threadIdx.x * kPer;
+    int8_t lab[kPer];
+    int c[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      lab[j] = n0 + j < N ? label[n0 + j] : (int8_t)-2;
+      c[0] += lab[j] != -2;
+      c[1] += lab[j] == 1;
+      c[2] += lab[j] == 0;
+    }
+    int incl[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const unsigned b = __ballot_sync(0xFFFFFFFFu, flag[q]);
-      rank[q] = __popc(b & ((1u << lane) - 1u));
-      if (lane == 0) s_warp[q][warp] = __popc(b);
+      incl[q] = c[q];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl[q], d);
+        if (lane >= d) incl[q] += t;
+      }
+      if (lane == 31) s_warp[q][warp] = incl[q];
     }
     __syncthreads();
     if (warp < 3) {
       const int v = s_warp[warp][lane];
-      int incl = v;
+      int in2 = v;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += t;
+        const int t = __shfl_up_sync(0xFFFFFFFFu, in2, d);
+        if (lane >= d) in2 += t;
       }
-      s_warp[warp][lane] = incl - v;   // exclusive prefix of the per-warp totals
-      if (lane == 31) s_tot[warp] = incl;
+      s_warp[warp][lane] = in2 - v;   // exclusive prefix of the per-warp totals
+      if (lane == 31) s_tot[warp] = in2;
     }
     __syncthreads();
-    if (flag[1]) w.fg_list[(size_t)f * N + s_base[1] + s_warp[1][warp] + rank[1]] = n;
-    if (flag[2]) w.bg_list[(size_t)f * N + s_base[2] + s_warp[2][warp] + rank[2]] = n;
+    int o1 = s_base[1] + s_warp[1][warp] + incl[1] - c[1];
+    int o2 = s_base[2] + s_warp[2][warp] + incl[2] - c[2];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (lab[j] == 1) w.fg_list[(size_t)f * N + o1++] = n0 + j;
+      if (lab[j] == 0) w.bg_list[(size_t)f * N + o2++] = n0 + j;
+    }
     __syncthreads();
     if (threadIdx.x < 3) s_base[threadIdx.x] += s_tot[threadIdx.x];
     __syncthreads();
