@@ -237,7 +237,7 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 //   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 3);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
 template <int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int nsteps,
             int row_bytes, int items_cap, Ws ws) {
   extern __shared__ int s_buckets[];   // [nb] counts, [nb] offsets, [nb] fill
@@ -1156,7 +1156,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<F, 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max,        \
+    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max,        \
                                                           p.nsteps, p.row_words * 4, items_cap, ws);              \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
