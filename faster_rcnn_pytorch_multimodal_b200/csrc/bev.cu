@@ -22,7 +22,7 @@
 //           voxel's rank in the reference's order;
 //   voxel   one warp per voxel: rank < max_voxels keeps it; if it has more than max_pts points the
 //           ones with fewer than max_pts smaller indices are the first max_pts in input order
-//           (rank-by-counting inside the bucket, voxels that dense are rare); max z, count and the
+//           (bisection on the index value over the bucket, O(cnt log n)); max z, count and the
 //           intensity / elongation sums are warp reductions; the height slice is written at once and
 //           the voxel's rank goes into a per-column atomicMax;
 //   meta    one thread per voxel: the voxel whose rank is the column maximum writes the meta channels.
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(int n, Ws w) {
   }
 }
 
-__global__ void __launch_bounds__(256) voxel_kernel(const float* __restrict__ pts, Grid g, Ws w, float* __restrict__ out,
-                                                     int32_t* __restrict__ num_voxels_out) {
+__global__ void __launch_bounds__(256) voxel_kernel(int n_points, const float* __restrict__ pts, Grid g, Ws w,
+                                                     float* __restrict__ out, int32_t* __restrict__ num_voxels_out) {
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const int nvox = w.counters[1];
@@ -200,15 +200,25 @@ __global__ void __launch_bounds__(256) voxel_kernel(const float* __restrict__ pt
     }
     const int k = w.vkey[v], cnt = w.cnt[k];
     const int32_t* b = w.bucket + w.base[k];
+    // More points than the voxel keeps: the first max_pts in input order are the max_pts smallest indices.
+    // Bisect on the index value (indices are distinct): the smallest `cut` with max_pts indices below it.
+    // O(cnt log n) per voxel, so a degenerate cloud (zero padding: every point in one voxel) stays cheap.
+    int cut = 0x7fffffff;
+    if (cnt > g.max_pts) {
+      int lo = 0, hi = n_points;               // count(idx < lo) < max_pts <= count(idx < hi)
+      while (hi - lo > 1) {
+        const int mid = lo + ((hi - lo) >> 1);
+        int below = 0;
+        for (int j = lane; j < cnt; j += 32) below += b[j] < mid;
+        below = (int)__reduce_add_sync(0xffffffffu, (unsigned)below);
+        if (below >= g.max_pts) hi = mid; else lo = mid;
+      }
+      cut = hi;
+    }
     float zmax = -INFINITY, si = 0.0f, se = 0.0f;
     for (int j = lane; j < cnt; j += 32) {
       const int idx = b[j];
-      bool take = true;
-      if (cnt > g.max_pts) {                   // keep the max_pts smallest indices = first in input order
-        int smaller = 0;
-        for (int q = 0; q < cnt; ++q) smaller += b[q] < idx;
-        take = smaller < g.max_pts;
-      }
+      const bool take = idx < cut;
       if (take) {
         const float* p = pts + (size_t)idx * g.n_feat;
         zmax = fmaxf(zmax, fsub(p[2], g.z_lo));
@@ -295,7 +305,7 @@ extern "C" int b2d_bev_rasterize(int num_points, int num_feat, const float* poin
   B2D_LAUNCHED();
   bev::scan_kernel<<<1, 1024, 0, st>>>(num_points, w);
   B2D_LAUNCHED();
-  bev::voxel_kernel<<<wgrid, 256, 0, st>>>(points, g, w, bev_map, num_voxels);
+  bev::voxel_kernel<<<wgrid, 256, 0, st>>>(num_points, points, g, w, bev_map, num_voxels);
   B2D_LAUNCHED();
   bev::meta_kernel<<<min(blocks, 4 * kNumSMs), 256, 0, st>>>(g, w, bev_map);
   B2D_LAUNCHED();

@@ -133,6 +133,24 @@ def test_gpu_dense_voxels_and_scale():
 
 
 @pytest.mark.gpu
+def test_gpu_degenerate_cloud_all_points_in_one_voxel():
+    """Zero-padded sweeps put tens of thousands of points into one voxel: must stay exact and fast."""
+    import time
+    c = B.LidarCfg()
+    pts = np.zeros((60000, 5), dtype=np.float32)
+    pts[:, 3] = np.linspace(0, 1, 60000, dtype=np.float32)
+    pts[::1000, :3] = [[10.0, 3.0, -1.0]]
+    _, want = B.lidar_bev_map(pts, 1.0, c)
+    _gpu_map(pts, c)                                   # warm-up (workspace allocation)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, got, nv = _gpu_map(pts, c)
+    assert time.perf_counter() - t0 < 0.5
+    assert nv == 2
+    _assert_map(got, want)
+
+
+@pytest.mark.gpu
 def test_gpu_no_points_inside():
     c = B.LidarCfg(x_range=(0, 4), y_range=(-2, 2))
     far = np.full((10, 5), 100.0, dtype=np.float32)
