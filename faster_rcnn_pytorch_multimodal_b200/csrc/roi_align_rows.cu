@@ -77,6 +77,12 @@ __device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait 
 #ifndef B2D_ROW_UNROLL
 #define B2D_ROW_UNROLL 1
 #endif
+#ifndef B2D_WHOLE_SLACK
+#define B2D_WHOLE_SLACK 2       /* = B2D_SLACK: whole-RoI items use the same span as split items (a wider span measured flat) */
+#endif
+#ifndef B2D_OBSERVE_ALL
+#define B2D_OBSERVE_ALL 0
+#endif
 #ifndef B2D_FFMA2
 #define B2D_FFMA2 1
 #endif
@@ -131,7 +137,7 @@ struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
   int lane_stride;  // words between channels of one slot (= 1 mod 32)
   int row_words;    // words per ring slot
-  int Rr, St, nblk, nbk, span_max, nsteps;
+  int Rr, St, nblk, nbk, span_max, span_whole, nsteps;
   size_t smem;
   bool ok;
 };
@@ -168,6 +174,10 @@ static Plan make_plan(int H, int W, bool allow_tma) {
     p.nsteps = ceil_div(H, St);
   }
   if (p.span_max > kMaxRows) p.span_max = kMaxRows;
+  // whole-RoI items may use all but B2D_WHOLE_SLACK blocks of the ring
+  p.span_whole = p.nblk > 1 ? (p.nblk - B2D_WHOLE_SLACK - 1) * p.St + 1 : p.span_max;
+  if (p.span_whole > kMaxRows) p.span_whole = kMaxRows;
+  if (p.span_whole < p.span_max) p.span_whole = p.span_max;
   p.smem = fixed + (size_t)p.Rr * row_bytes;
   p.ok = p.span_max >= 4 && p.nblk <= kMaxBlk;
   return p;
@@ -198,8 +208,30 @@ static Ws carve(void* base, int F, int per_frame, int H) {
 
 // ------------------------------------------------------------------------------------------
 // Items of one RoI.  Calls emit(ph0, nph, first_row, last_row, slow) for each item, in ph order.
+// A RoI whose sample rows all fit in `span_whole` rows stays ONE item (it leaves through the bulk-store tile,
+// which is worth a tighter window); otherwise it is cut into items of at most span_max rows.
 template <int S, class Emit>
-__device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_max, Emit emit) {
+__device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_max, int span_whole, Emit emit) {
+  if (span_whole > span_max) {
+    int wf = H, wl = -1;
+    for (int ph = 0; ph < kP; ph += kP - 1)
+      for (int iy = 0; iy < S; ++iy) {
+        const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
+        if (t.ok) {
+          wf = min(wf, t.lo);
+          wl = max(wl, t.hi);
+        }
+      }
+    // (rows are monotone in ph: the first and the last bin-row bound the RoI; a RoI with invalid outer
+    // samples is left to the general walk below)
+    bool all_ok = true;
+    for (int ph = 0; ph < kP; ++ph)
+      for (int iy = 0; iy < S; ++iy) all_ok &= axis_tap(g.start_h, g.bin_h, ph, iy, S, H).ok;
+    if (all_ok && wl - wf + 1 > span_max && wl - wf + 1 <= span_whole) {
+      emit(0, kP, wf, wl, false);
+      return;
+    }
+  }
   int a = 0, cf = H, cl = -1;
   for (int ph = 0; ph < kP; ++ph) {
     int rf = H, rl = -1;
@@ -231,14 +263,15 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 }
 
 // Record of one item (float4 units):
-//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16 | narrow << 17, bucket, -}
+//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16 | narrow << 17, bucket (block of the first row),
+//              block of the last row}
 //   [1..11]   14 column taps x 3 words {byte offset of the lo column, hx, lx}; the hi column is lo + 1
 //             (narrow items, code bit 17: [1..7] = 7 bins x {byte offset of the base column, w0, w1, w2})
 //   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 3);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
 template <int S>
 __global__ void __launch_bounds__(512)
-prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int nsteps,
+prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int span_whole, int nsteps,
             int row_bytes, int items_cap, Ws ws) {
   extern __shared__ int s_buckets[];   // [nb] counts, [nb] offsets, [nb] fill
   const int nb = nsteps + 1;
@@ -261,7 +294,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     if (!L.seg_count && (int)roi[0] != f) continue;
     const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
     const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
-    for_each_item<S>(g, H, span_max, [&](int, int, int cf, int cl, bool slow) {
+    for_each_item<S>(g, H, span_max, span_whole, [&](int, int, int cf, int cl, bool slow) {
       const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
       atomicAdd(&cnt[b], 1);
     });
@@ -289,7 +322,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
     const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
     const float inv_cnt = 1.0f / g.count;
-    for_each_item<S>(g, H, span_max, [&](int ph0, int nph, int cf, int cl, bool slow) {
+    for_each_item<S>(g, H, span_max, span_whole, [&](int ph0, int nph, int cf, int cl, bool slow) {
       const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
       float4* rec = recs + (size_t)(offs[b] + atomicAdd(&fill[b], 1)) * kRecVec;
       // column taps.  Invalid samples carry zero weights and point at column 0 (always resident);
@@ -394,7 +427,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
         }
       }
       const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16) | ((narrow ? 1 : 0) << 17);
-      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(b), 0.f);
+      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(b), __int_as_float(cl < 0 ? 0 : cl / St));
     });
   }
 }
@@ -1014,7 +1047,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     if (!((code >> 16) & 1)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       release(bucket);
-      observe(min(bucket + nbk, nsteps));
+      // only the blocks the item reads have to be there (B2D_OBSERVE_ALL: the whole window, as before)
+      const int last_blk = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.w));
+      observe(min(B2D_OBSERVE_ALL ? bucket + nbk : last_blk + 1, nsteps));
       // once the rows of this item are done the warp only needs what its NEXT item needs (already
       // claimed, record in flight since the top of the loop): publish that bucket before the output
       // phase so the producer can refill while this warp stages and stores
@@ -1156,7 +1191,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max,        \
+    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole,   \
                                                           p.nsteps, p.row_words * 4, items_cap, ws);              \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
