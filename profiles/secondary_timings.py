@@ -89,6 +89,13 @@ m = MultiScaleRoIAlign(list(feats), 7, 2)
 boxes = rois[0, :300, 1:].contiguous()
 out["fpn_multiscale_crop_300_ms"] = timed(lambda: m(feats, [boxes], [(1280, 1920)]))
 
+# ---- configs[3]: RPN on FPN level p2 of a Waymo frame (320 x 480 x 25 = 3.84 M anchors at stride 4), 6000 -> 300
+c2 = dict(bench.CFG, Hf=320, Wf=480, C=1)
+anchors_p2, _ = generate_anchors_pre(320, 480, 4, bench.SCALES, bench.RATIOS, 1.0, device=dev)
+prob2, deltas2, _, info2 = bench.synth_frames(c2, 1, dev, 0)
+out["proposal_layer_fpn_p2_3p84M_anchors_ms"] = timed(lambda: ops.proposal_batched(prob2, deltas2, info2, anchors_p2, None, 25, 6000, 300, 0.7))
+del prob2, deltas2, anchors_p2
+
 # ---- uncertainty: T = 20 MC samples, 300 RoIs, K*E = 14; final filter for 64 frames
 mc = torch.randn(20, 300, 14, device=dev)
 out["mc_bbox_var_T20_ms"] = timed(lambda: loss_utils.compute_bbox_var(mc))
