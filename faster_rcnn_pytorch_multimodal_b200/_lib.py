@@ -33,6 +33,7 @@ PROTOTYPES = {
     "b2d_argsort_desc": (I, [I, I, _f, _i, _v]),
     "b2d_roi_align_workspace_bytes": (SZ, [I, I, I, I, I, I]),
     "b2d_roi_align_forward": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, _f, _v, SZ, _v]),
+    "b2d_roi_align_forward_route": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, I, _f, _v, SZ, _v]),
     "b2d_roi_align_backward": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, I, _f, _v, SZ, _v]),
     "b2d_roi_align_forward_levels": (I, [I, I, I, _v, _i, _i, _v, _f, _i, I, I, I, I, I, _f, _v]),
     "b2d_fpn_level_map": (I, [I, _f, I, I, F32, I, F32, _i, _v]),
@@ -70,8 +71,7 @@ class B2DError(RuntimeError):
     pass
 
 
-def lib():
-    """Load (once) and return the ctypes handle; raises if the CUDA library is absent."""
+def _load():
     global _lib
     if _lib is None:
         with _lock:
@@ -89,9 +89,46 @@ def lib():
     return _lib
 
 
+class _OnDevice:
+    """The library handle with every call made under ``torch.cuda.device(device)``.
+
+    The C ABI launches on the calling thread's CURRENT device (kernel launches, cudaFuncSetAttribute,
+    cudaMemsetAsync), while the stream and the pointers it is given belong to the tensors' device; torchvision's
+    ops switch devices with a guard, and so does every wrapper in this package."""
+
+    __slots__ = ("_h", "_dev")
+
+    def __init__(self, handle, device):
+        self._h, self._dev = handle, device
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        dev = self._dev
+
+        def guarded(*args):
+            with torch.cuda.device(dev):
+                return fn(*args)
+
+        return guarded
+
+
+def lib(device=None):
+    """Load (once) and return the ctypes handle; raises if the CUDA library is absent.  With ``device`` (a CUDA
+    torch.device) the returned handle makes that device current around every call."""
+    handle = _load()
+    if device is None:
+        return handle
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise B2DError("b2d glue runs on CUDA devices only (no CPU fallback)")
+    if device.index is None or device.index == torch.cuda.current_device():
+        return handle
+    return _OnDevice(handle, device)
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
-        L = lib()
+        L = _load()
         msg = L.b2d_status_string(rc).decode()
         if rc == -3:
             msg += f" (cudaError {L.b2d_last_cuda_error()})"
@@ -108,9 +145,16 @@ def stream_ptr(device=None):
 
 
 def require_cuda(*tensors):
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise B2DError("b2d glue runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise B2DError(f"b2d glue: tensors on different devices ({dev} and {t.device})")
 
 
 def f32c(t):
@@ -120,18 +164,38 @@ def f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def i32c(t, what="index tensor"):
+    """contiguous int32 view/copy of an integer tensor (the kernels read int32); None passes through."""
+    if t is None:
+        return None
+    if t.dtype == torch.int32:
+        return t if t.is_contiguous() else t.contiguous()
+    if t.dtype in (torch.int64, torch.int16, torch.int8, torch.uint8):
+        return t.to(torch.int32).contiguous()
+    raise B2DError(f"{what} must be an integer tensor, got {t.dtype}")
+
+
 class _Workspaces:
-    """Per-(device, tag) cached byte buffers (the caller owns all memory the library uses)."""
+    """Cached scratch buffers, one per (device, stream, tag): the caller owns all memory the library uses.
+
+    Keyed by the CURRENT stream so that calls overlapped on two streams (camera and lidar branches) never
+    share scratch; a buffer is only ever used on the stream it was allocated on, so the caching allocator's
+    stream-ordered reuse rules hold without record_stream()."""
 
     def __init__(self):
         self._bufs = {}
+        self._lock = threading.Lock()
 
     def get(self, device, tag, nbytes):
-        key = (str(device), tag)
-        buf = self._bufs.get(key)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self._bufs[key] = buf
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream(device).cuda_stream, tag)
+        with self._lock:
+            buf = self._bufs.get(key)
+            if buf is None or buf.numel() < nbytes:
+                with torch.cuda.device(idx):
+                    buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+                self._bufs[key] = buf
         return buf
 
 

@@ -19,24 +19,18 @@
 // one thread per channel.  A thread is the only writer of its channel plane, RoIs are
 // visited in index order, so accumulation is deterministic with no atomics at all; each
 // grad_feat element is written to HBM exactly once.
-#include <stdlib.h>
-
 #include "roi_common.cuh"
 
 namespace b2d {
 
-size_t sweep_workspace_bytes(int F, int H, int n_list, int per_frame);
 size_t rows_workspace_bytes(int F, int H, int per_frame);
 size_t bwd_rows_workspace_bytes(int n_list);
 int roi_align_backward_rows(int F, int C, int H, int W, const float* grad_out, const RoiList& L, int PH, int PW,
                             float scale, int S, int aligned, int accumulate, float* grad_feat, void* workspace,
                             size_t workspace_bytes, cudaStream_t st);
 int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
-                           float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
-                           cudaStream_t st);
-int roi_align_forward_sweep(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
-                            float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
-                            cudaStream_t st);
+                           float scale, int S, int aligned, bool coop_fill, float* out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 template <int CPB>
@@ -341,37 +335,47 @@ using namespace b2d;
 extern "C" size_t b2d_roi_align_workspace_bytes(int F, int /*C*/, int H, int /*W*/, int num_rois, int per_frame) {
   if (F <= 0 || H <= 0 || num_rois <= 0) return 0;
   if (per_frame <= 0 || per_frame > num_rois) per_frame = num_rois;
-  const size_t a = sweep_workspace_bytes(F, H, num_rois, per_frame), b = rows_workspace_bytes(F, H, per_frame);
-  const size_t c = bwd_rows_workspace_bytes(num_rois);
-  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+  const size_t b = rows_workspace_bytes(F, H, per_frame), c = bwd_rows_workspace_bytes(num_rois);
+  return b > c ? b : c;
 }
 
-extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
-                                     const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
-                                     int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, float* out,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+// Rows of RoIs whose batch index is outside [0, F) are written by no CTA of the frame-parallel kernels:
+// they come back as zeros (plain [R,5] lists only; padded per-frame segments carry no batch index).
+__global__ void __launch_bounds__(256) zero_foreign_rows_kernel(RoiList L, int F, int per_roi, float* __restrict__ out) {
+  const int e = blockIdx.x;
+  const int r = L.ids ? L.ids[e] : e;
+  const float b = L.rois[(size_t)r * 5];
+  if (b >= 0.0f && (int)b < F) return;
+  float* o = out + (size_t)r * per_roi;
+  for (int i = threadIdx.x; i < per_roi; i += blockDim.x) o[i] = 0.0f;
+}
+
+static int roi_align_forward_impl(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
+                                  const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
+                                  int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, int route,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream) {
   if (F <= 0 || C <= 0 || H <= 0 || W <= 0 || PH <= 0 || PW <= 0 || !feat || !out) return B2D_ERR_INVALID_ARG;
+  if (route < B2D_ROI_ROUTE_AUTO || route > B2D_ROI_ROUTE_GATHER) return B2D_ERR_INVALID_ARG;
   RoiList L{rois, roi_ids, roi_ids ? n_roi_ids : num_rois, seg_count, seg_stride};
   if (seg_count && (seg_stride <= 0 || (long long)seg_stride * F > L.n)) return B2D_ERR_INVALID_ARG;
   if (L.n <= 0) return B2D_OK;
   if (!rois) return B2D_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const long long total = (long long)L.n * C * PH * PW;
+  if (!seg_count) {
+    zero_foreign_rows_kernel<<<L.n, 256, 0, st>>>(L, F, C * PH * PW, out);
+    B2D_LAUNCHED();
+  }
   // Few RoIs on few channel groups (one FPN level of one frame: ~75 RoIs x 256 channels): the streaming
   // kernels would run 8-32 CTAs and pull the whole level through shared memory for a handful of RoIs
   // (p3 160x240: 325 us); one thread per output straight from L2 takes 20-45 us.  The gather kernel costs
   // ~30 ps per output, the streaming kernels ~2.5 ps at full occupancy.
-  // (B2D_ROI_NO_GATHER: test knob, keeps small test shapes on the streaming kernels)
-  const bool sparse = total <= (1LL << 22) && (long long)ceil_div(C, 32) * F < kNumSMs / 2 && !getenv("B2D_ROI_NO_GATHER");
-  // production path: 7x7 "rows" kernel (roi_align_rows.cu), then the generic sweep kernel; both need the workspace
-  if (C >= 16 && !sparse) {
-    const int rc = roi_align_forward_rows(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
-                                          workspace, workspace_bytes, st);
-    if (rc != B2D_ERR_UNSUPPORTED) return rc;
-  }
-  if (C >= 16 && !sparse) {
-    const int rc = roi_align_forward_sweep(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned, out,
-                                           workspace, workspace_bytes, st);
+  const bool sparse = route == B2D_ROI_ROUTE_GATHER ||
+                      (route == B2D_ROI_ROUTE_AUTO && total <= (1LL << 22) && (long long)ceil_div(C, 32) * F < kNumSMs / 2);
+  // production path: the 7x7 "rows" kernel (roi_align_rows.cu); needs the workspace
+  if (C >= 16 && !sparse && route != B2D_ROI_ROUTE_PLANES) {
+    const int rc = roi_align_forward_rows(F, C, H, W, feat, L, PH, PW, spatial_scale, sampling_ratio, aligned,
+                                          route == B2D_ROI_ROUTE_ROWS_COOP, out, workspace, workspace_bytes, st);
     if (rc != B2D_ERR_UNSUPPORTED) return rc;
   }
   const size_t plane = (size_t)H * W * sizeof(float);
@@ -397,6 +401,24 @@ extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* fe
                                                            aligned, out);
   B2D_LAUNCHED();
   return B2D_OK;
+}
+
+extern "C" int b2d_roi_align_forward(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
+                                     const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
+                                     int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, float* out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return roi_align_forward_impl(F, C, H, W, feat, rois, num_rois, roi_ids, n_roi_ids, seg_count, seg_stride, PH, PW,
+                                spatial_scale, sampling_ratio, aligned, B2D_ROI_ROUTE_AUTO, out, workspace, workspace_bytes,
+                                stream);
+}
+
+extern "C" int b2d_roi_align_forward_route(int F, int C, int H, int W, const float* feat, const float* rois, int num_rois,
+                                           const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count,
+                                           int seg_stride, int PH, int PW, float spatial_scale, int sampling_ratio,
+                                           int aligned, int route, float* out, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  return roi_align_forward_impl(F, C, H, W, feat, rois, num_rois, roi_ids, n_roi_ids, seg_count, seg_stride, PH, PW,
+                                spatial_scale, sampling_ratio, aligned, route, out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b2d_roi_align_forward_levels(int num_levels, int F, int C, const float* const* feats, const int32_t* heights,

@@ -17,8 +17,8 @@
 //     A 5x5-pixel RoI costs 5 rows x 28 taps = 140 wavefronts instead of 784; only RoIs whose bins
 //     are taller than two pixels still pay 16 taps per output (their samples share nothing).
 //
-// Data flow per CTA = (32-channel group, frame[, item split]).  The CTA streams the feature rows of
-// its 32 channels top to bottom through a ring of nblk blocks of St rows.  Lane c reads pixel
+// Data flow per CTA = (32-channel group, frame, part of the frame's RoIs).  The CTA streams the feature
+// rows of its 32 channels top to bottom through a ring of nblk blocks of St rows.  Lane c reads pixel
 // (row, x) of channel c at word  slot*row_words + c*lane_stride + x  with an ODD lane_stride (W + 1 for
 // even W), so the 32 lanes of a tap always hit 32 different banks.
 //
@@ -40,20 +40,27 @@
 // sorted by first row; warps claim items from a shared counter and prefetch the next record while they
 // compute.
 //
-// Output.  A whole-RoI item (nph = 7) of a full channel group is 6272 contiguous bytes of the output:
-// the warp try-locks one of kPool shared tiles, writes its 49 values per lane there and ONE bulk copy
-// (cp.async.bulk shared -> global) stores the slice - no LDS/STG round trip, half of all output bytes on
-// the bench workload.  Everything else is staged one bin-row [32 ch][7] at a time so that global stores
-// run along (c, pw).
+// Output (the phase that bounds the kernel: a build that computes nothing and only writes the 60 MB of
+// pooled features per frame runs within 3 % of the full kernel).  Only whole [32 ch][49] slices of the
+// output - 6272 contiguous bytes - leave at memory speed; 28-byte runs 196 bytes apart (one bin-row of 32
+// channels) cost five times as much per byte on the store path.  So EVERY RoI leaves as a whole slice:
+//   * a RoI that is ONE item (all sample rows inside the window): the warp try-locks one of kPool shared
+//     tiles, writes its 49 values per lane there and ONE bulk copy (cp.async.bulk shared -> global) stores
+//     the slice;
+//   * a RoI split over several windows: each item stores its bin-rows TRANSPOSED, [bin][32 ch], into the
+//     RoI's own output slice - fully coalesced 128-byte stores, the slice doubles as the assembly buffer and
+//     stays in L2 - and counts itself done on a per-RoI shared-memory counter; the warp that completes the
+//     count reads the slice back (L2), transposes it through a pool tile and bulk-stores it in place.
+// Ragged channel groups, unaligned outputs and the cp.async variant stage one bin-row [32 ch][7] at a time
+// so that global stores run along (c, pw).
 //
 // Two things ptxas must be told (each cost 10 % when missed): (1) every branch on a warp-uniform value
 // goes through a warp reduction (CREDUX -> uniform register); one branch it takes for divergent - the
 // producer/consumer split on threadIdx.x >> 5, a plain `held >= 0` - and every tap of the consumers
 // loses its [column + uniform row + imm] addressing to a per-tap IADD; (2) code size: the item code
-// is instantiated for 2, 4 and 7 accumulator rows only - one variant per nph, or per nph x {3-tap narrow
-// bins, 4-tap}, falls out of the instruction cache (4500+ instructions: 46 us/frame instead of 42).
+// is instantiated for 2, 4 and 7 accumulator rows only - one variant per nph falls out of the instruction
+// cache (4500+ instructions: 46 us/frame instead of 42).
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "roi_common.cuh"
@@ -62,53 +69,18 @@ namespace b2d {
 
 namespace rows {
 
-#ifdef B2D_ROWS_TIMING
-__device__ unsigned long long g_dbg[8];   // [0] total, [1] wait full, [2] wait done, [3] run_item, [4] items, [5] producer wait done, [6] producer wait stg, [7] producer total
-#define DBG_T0(v) long long v = clock64()
-#define DBG_ACC(slot, v) dbg_acc[slot] += clock64() - v
-#else
-#define DBG_T0(v)
-#define DBG_ACC(slot, v)
-#endif
-
+// A/B build knobs (profiles/ only; the shipped library is built without any -D)
 #ifndef B2D_STAGES
 #define B2D_STAGES 2
 #endif
-#ifndef B2D_ROW_UNROLL
-#define B2D_ROW_UNROLL 1
-#endif
-#ifndef B2D_WHOLE_SLACK
-#define B2D_WHOLE_SLACK 2       /* = B2D_SLACK: whole-RoI items use the same span as split items (a wider span measured flat) */
-#endif
-#ifndef B2D_OBSERVE_ALL
-#define B2D_OBSERVE_ALL 0
-#endif
-#ifndef B2D_FFMA2
-#define B2D_FFMA2 1
-#endif
-#ifndef B2D_TAP_PIPE
-#define B2D_TAP_PIPE 0
-#endif
-#ifndef B2D_TAP_PIPE_MAX_NPH
-#define B2D_TAP_PIPE_MAX_NPH 4
-#endif
-#ifndef B2D_NARROW
-#define B2D_NARROW 0
-#endif
-#ifndef B2D_OUT_TILES
-#define B2D_OUT_TILES 1
-#endif
-#ifndef B2D_EARLY
-#define B2D_EARLY 0
+#ifndef B2D_POOL
+#define B2D_POOL 3
 #endif
 #ifndef B2D_SLACK
 #define B2D_SLACK 2
 #endif
-#ifndef B2D_WARPS
-#define B2D_WARPS 10
-#endif
-constexpr int kRowUnroll = B2D_ROW_UNROLL;   // row loop of an item: 1 keeps the 14 item variants inside the instruction cache
-constexpr int kWarps = B2D_WARPS;
+
+constexpr int kWarps = 10;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
 constexpr int kP = 7;              // PH = PW = 7
@@ -118,26 +90,20 @@ constexpr int kMaxRows = 10;       // distinct feature rows per item
 constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
+constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each takes the RoIs e % split == part
+constexpr int kMaxCount = 4096;    // RoIs per frame the per-RoI completion counters cover (one byte each)
 
-#ifndef B2D_POOL
-#define B2D_POOL 2
-#endif
-constexpr int kPool = B2D_POOL;             // TMA fill: whole-RoI output tiles [32 ch][49] shared by the consumer warps
+constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps
 constexpr int kTileWords = kCh * kP * kP;
 constexpr int kStages = B2D_STAGES;         // staging rows of the TMA fill
-#ifndef B2D_PRODUCERS
-#define B2D_PRODUCERS 2
-#endif
-#ifndef B2D_REPACK_PIPE
-#define B2D_REPACK_PIPE 0
-#endif
-constexpr int kProducers = B2D_PRODUCERS;   // producer warps of the TMA fill (each repacks 32 / kProducers channels)
+constexpr int kProducers = 2;               // producer warps of the TMA fill (each repacks 32 / kProducers channels)
 
 struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
-  int lane_stride;  // words between channels of one slot (= 1 mod 32)
+  int lane_stride;  // words between channels of one slot (odd)
   int row_words;    // words per ring slot
   int Rr, St, nblk, nbk, span_max, span_whole, nsteps;
+  int cnt_bytes;    // per-RoI completion counters (0: split RoIs take the bin-row store path)
   size_t smem;
   bool ok;
 };
@@ -147,7 +113,7 @@ struct Plan {
 // with that per-row shift.
 static int stage_width(int W) { return W % 4 == 0 ? W : (W + 3) / 4 * 4 + 4; }
 
-static Plan make_plan(int H, int W, bool allow_tma) {
+static Plan make_plan(int H, int W, int per_frame, bool allow_tma) {
   Plan p{};
   p.fill = (allow_tma && (H * W) % 4 == 0 && stage_width(W) <= 256) ? 1 : 0;
   const int pitch = (W + 1) | 1;                     // smallest ODD value >= W + 1: any odd pitch maps 32 channels to 32 banks
@@ -155,9 +121,10 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   p.row_words = kCh * pitch;
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * stage_width(W) * 4 : 0;
-  const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and an output tile
+  const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and a bin-row tile
   const size_t pool = p.fill ? (size_t)kPool * kTileWords * 4 : 0;
-  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * B2D_OUT_TILES * kCh * kP * 4 + 256 + staging + pool;
+  p.cnt_bytes = (p.fill && per_frame <= kMaxCount) ? (int)align_up((size_t)per_frame, 16) : 0;
+  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * kCh * kP * 4 + 256 + staging + pool + p.cnt_bytes;
   const size_t budget = 227 * 1024 - 1280;       // 1.2 KB of static shared memory (barriers, locks, counters)
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
@@ -174,8 +141,8 @@ static Plan make_plan(int H, int W, bool allow_tma) {
     p.nsteps = ceil_div(H, St);
   }
   if (p.span_max > kMaxRows) p.span_max = kMaxRows;
-  // whole-RoI items may use all but B2D_WHOLE_SLACK blocks of the ring
-  p.span_whole = p.nblk > 1 ? (p.nblk - B2D_WHOLE_SLACK - 1) * p.St + 1 : p.span_max;
+  // whole-RoI items may use all but two blocks of the ring (+ the one the producer fills)
+  p.span_whole = p.nblk > 1 ? (p.nblk - 2 - 1) * p.St + 1 : p.span_max;
   if (p.span_whole > kMaxRows) p.span_whole = kMaxRows;
   if (p.span_whole < p.span_max) p.span_whole = p.span_max;
   p.smem = fixed + (size_t)p.Rr * row_bytes;
@@ -184,14 +151,14 @@ static Plan make_plan(int H, int W, bool allow_tma) {
 }
 
 struct Ws {
-  float4* records;        // [F][items_cap][kRecVec]
-  int32_t* bucket_start;  // [F][nb + 2]
+  float4* records;        // [F][items_cap][kRecVec], grouped by part, sorted by first row within a part
+  int32_t* part_start;    // [F][kMaxSplit + 1]
   float scale;
   int aligned;
   size_t bytes;
 };
 
-static Ws carve(void* base, int F, int per_frame, int H) {
+static Ws carve(void* base, int F, int per_frame) {
   Ws w{};
   size_t off = 0;
   char* p = static_cast<char*>(base);
@@ -201,13 +168,14 @@ static Ws carve(void* base, int F, int per_frame, int H) {
     return r;
   };
   w.records = reinterpret_cast<float4*>(take((size_t)F * per_frame * kP * kRecBytes));
-  w.bucket_start = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * (H + 4)));
+  w.part_start = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * (kMaxSplit + 1)));
   w.bytes = off;
   return w;
 }
 
 // ------------------------------------------------------------------------------------------
-// Items of one RoI.  Calls emit(ph0, nph, first_row, last_row, slow) for each item, in ph order.
+// Items of one RoI.  Calls emit(ph0, nph, first_row, last_row, slow) for each item, in ph order; the items
+// cover the 7 bin-rows exactly once.
 // A RoI whose sample rows all fit in `span_whole` rows stays ONE item (it leaves through the bulk-store tile,
 // which is worth a tighter window); otherwise it is cut into items of at most span_max rows.
 template <int S, class Emit>
@@ -263,30 +231,32 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 }
 
 // Record of one item (float4 units):
-//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16 | narrow << 17, bucket (block of the first row),
-//              block of the last row}
-//   [1..11]   14 column taps x 3 words {byte offset of the lo column, hx, lx}; the hi column is lo + 1
-//             (narrow items, code bit 17: [1..7] = 7 bins x {byte offset of the base column, w0, w1, w2})
-//   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 3);
+//   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16, block of the first row (bucket) | block of the
+//              last row << 16, index of the RoI in its frame's list | items of the RoI << 24}
+//   [1..11]   14 column taps: 14 byte offsets of the lo column (the hi column is lo + 1), then the weights;
+//             S == 2: per bin pair (2j, 2j+1) the weights of tap a / b of the first sample and c / d of the second
+//             as aligned register pairs, then bin 6;  S == 1: {offset, hx, lx} triples
+//   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 2);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
 template <int S>
 __global__ void __launch_bounds__(512)
 prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int span_whole, int nsteps,
-            int row_bytes, int items_cap, Ws ws) {
-  extern __shared__ int s_buckets[];   // [nb] counts, [nb] offsets, [nb] fill
+            int row_bytes, int items_cap, int split, Ws ws) {
+  extern __shared__ int s_buckets[];   // [split * nb] counts, offsets, fill
   const int nb = nsteps + 1;
+  const int nkey = split * nb;
   int* cnt = s_buckets;
-  int* offs = s_buckets + nb;
-  int* fill = s_buckets + 2 * nb;
+  int* offs = s_buckets + nkey;
+  int* fill = s_buckets + 2 * nkey;
   const int f = blockIdx.x;
-  for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) s_buckets[i] = 0;
+  for (int i = threadIdx.x; i < 3 * nkey; i += blockDim.x) s_buckets[i] = 0;
   __syncthreads();
   int first = 0, n_ent = L.n;
   if (L.seg_count) {
     first = f * L.seg_stride;
     n_ent = L.seg_count[f];
   }
-  // pass A: bucket histogram
+  // pass A: (part, bucket) histogram
   for (int i = threadIdx.x; i < n_ent; i += blockDim.x) {
     const int e = first + i;
     const int r = L.ids ? L.ids[e] : e;
@@ -294,22 +264,22 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     if (!L.seg_count && (int)roi[0] != f) continue;
     const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
     const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
+    const int part = i % split;
     for_each_item<S>(g, H, span_max, span_whole, [&](int, int, int cf, int cl, bool slow) {
       const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
-      atomicAdd(&cnt[b], 1);
+      atomicAdd(&cnt[part * nb + b], 1);
     });
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
-    int32_t* bs = ws.bucket_start + (size_t)f * (nb + 2);
-    for (int b = 0; b < nb; ++b) {
-      offs[b] = run;
-      bs[b] = run;
-      run += cnt[b];
+    int32_t* ps = ws.part_start + (size_t)f * (kMaxSplit + 1);
+    for (int k = 0; k < nkey; ++k) {
+      if (k % nb == 0) ps[k / nb] = run;
+      offs[k] = run;
+      run += cnt[k];
     }
-    bs[nb] = run;
-    bs[nb + 1] = run;
+    for (int p = split; p <= kMaxSplit; ++p) ps[p] = run;
   }
   __syncthreads();
   // pass B: records
@@ -322,79 +292,52 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
     const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
     const float inv_cnt = 1.0f / g.count;
+    const int part = i % split;
+    int n_items = 0;
+    for_each_item<S>(g, H, span_max, span_whole, [&](int, int, int, int, bool) { ++n_items; });
+    // column taps (the same for every item of the RoI).  Invalid samples carry zero weights and point at
+    // column 0 (always resident); at the clamped right border lx is 0 and the hi tap reads whatever follows
+    // the row (finite).
+    float xw[4 * kXVec];
+    {
+      int xo[2 * kP];
+      float hx[2 * kP], lx[2 * kP];
+      for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
+        xo[k] = 0;
+        hx[k] = lx[k] = 0.0f;
+        if (k < kP * S) {
+          const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
+          if (t.ok) {
+            xo[k] = t.lo * 4;
+            hx[k] = t.wlo;
+            lx[k] = t.whi;
+          }
+        }
+      }
+      if (S == 2) {
+        for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
+        xw[14] = xw[15] = 0.0f;
+        for (int j = 0; j < 3; ++j) {
+          float* q = xw + 16 + 8 * j;
+          q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
+          q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
+          q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
+          q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
+        }
+        xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
+      } else {
+        for (int k = 0; k < 2 * kP; ++k) {
+          xw[3 * k] = __int_as_float(xo[k]);
+          xw[3 * k + 1] = hx[k];
+          xw[3 * k + 2] = lx[k];
+        }
+        xw[42] = xw[43] = 0.0f;
+      }
+    }
     for_each_item<S>(g, H, span_max, span_whole, [&](int ph0, int nph, int cf, int cl, bool slow) {
       const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
-      float4* rec = recs + (size_t)(offs[b] + atomicAdd(&fill[b], 1)) * kRecVec;
-      // column taps.  Invalid samples carry zero weights and point at column 0 (always resident);
-      // at the clamped right border lx is 0 and the hi tap reads whatever follows the row (finite).
-      float* xw = reinterpret_cast<float*>(rec + 1);
-      // "narrow" items (S == 2): the two samples of every bin fall within three consecutive pixel columns
-      // (bins up to two pixels wide), so the bin needs 3 taps per row {base, base+1, base+2} with merged
-      // weights instead of 4: record = 7 x {byte offset of base, w0, w1, w2}.
-      bool narrow = B2D_NARROW && S == 2 && W >= 3;
-      if (narrow) {
-        for (int pw = 0; pw < kP; ++pw) {
-          int base = W, top = -1;
-          AxisTap t[2];
-          for (int ix = 0; ix < 2; ++ix) {
-            t[ix] = axis_tap(g.start_w, g.bin_w, pw, ix, S, W);
-            if (t[ix].ok) {
-              base = min(base, t[ix].lo);
-              top = max(top, t[ix].hi);
-            }
-          }
-          if (top < 0) base = 0;
-          if (top - base > 2) narrow = false;
-          base = min(base, W - 2);                       // base + 2 <= W: the zeroed pad column at worst
-          float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          for (int ix = 0; ix < 2; ++ix)
-            if (t[ix].ok) {
-              w[min(t[ix].lo - base, 3)] += t[ix].wlo;
-              w[min(t[ix].hi - base, 3)] += t[ix].whi;
-            }
-          xw[4 * pw] = __int_as_float(base * 4);
-          xw[4 * pw + 1] = w[0];
-          xw[4 * pw + 2] = w[1];
-          xw[4 * pw + 3] = w[2];
-        }
-      }
-      if (!narrow) {
-        int xo[2 * kP];
-        float hx[2 * kP], lx[2 * kP];
-        for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
-          xo[k] = 0;
-          hx[k] = lx[k] = 0.0f;
-          if (k < kP * S) {
-            const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
-            if (t.ok) {
-              xo[k] = t.lo * 4;
-              hx[k] = t.wlo;
-              lx[k] = t.whi;
-            }
-          }
-        }
-        if (S == 2 && B2D_FFMA2) {
-          // pair layout for the packed contraction: 14 offsets, then per bin pair (2j, 2j+1) the weights of
-          // tap a / b of the first sample and c / d of the second as aligned register pairs, then bin 6
-          for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
-          xw[14] = xw[15] = 0.0f;
-          for (int j = 0; j < 3; ++j) {
-            float* q = xw + 16 + 8 * j;
-            q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
-            q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
-            q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
-            q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
-          }
-          xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
-        } else {
-          for (int k = 0; k < 2 * kP; ++k) {
-            xw[3 * k] = __int_as_float(xo[k]);
-            xw[3 * k + 1] = hx[k];
-            xw[3 * k + 2] = lx[k];
-          }
-          xw[42] = xw[43] = 0.0f;
-        }
-      }
+      float4* rec = recs + (size_t)(offs[part * nb + b] + atomicAdd(&fill[part * nb + b], 1)) * kRecVec;
+      for (int v = 0; v < kXVec; ++v) rec[1 + v] = make_float4(xw[4 * v], xw[4 * v + 1], xw[4 * v + 2], xw[4 * v + 3]);
       // distinct feature rows of the item and their weights per bin-row
       int nrows = 0;
       if (!slow) {
@@ -426,8 +369,10 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
           if (rv == 2) rec[kRowVec0 + j * rv + 1] = make_float4(wy[j][3], wy[j][4], wy[j][5], wy[j][6]);
         }
       }
-      const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16) | ((narrow ? 1 : 0) << 17);
-      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(b), __int_as_float(cl < 0 ? 0 : cl / St));
+      const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
+      const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
+      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks),
+                           __int_as_float((i & 0xFFFFFF) | (n_items << 24)));
     });
   }
 }
@@ -482,11 +427,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Output tile pool of the TMA variant: kPool whole-RoI tiles [32 ch][49].  A whole-RoI item of a full channel
-// group TRIES to take a tile (one pass over the locks, no waiting): with a tile the 49 values of each lane go
-// to shared memory once and leave with ONE bulk store of 6272 contiguous bytes - no LDS/STG round trip; the
-// tile stays locked until the copy has read it (released at the warp's next item).  Without one the item
-// takes the regular bin-row path.
+// Output tile pool of the TMA variant: kPool tiles [32 ch][49].  A warp with a whole slice to store TRIES to
+// take a tile (one pass over the locks, no waiting - a warp that blocked here would stop publishing its
+// progress and could starve the fill the tile holders are waiting on): with a tile the 49 values of each lane
+// go to shared memory once and leave with ONE bulk store of 6272 contiguous bytes; the tile stays locked until
+// the copy has read it (released at the warp's next item).
 __device__ __forceinline__ int tile_try_acquire(int* locks, int warp, int lane) {
   unsigned t = 0;                          // tile index + 1, 0 = none
   if (lane == 0) {
@@ -514,27 +459,22 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 
 // One item: nph = NPH bin-rows of one RoI for this lane's channel.
 // NPH is the variant (2, 4 or 7 accumulator rows), nph <= NPH the bin-rows the item really has: the rows in
-// between carry zero weights and are not stored.  (One variant per nph, times narrow / wide, does not fit
-// the instruction cache: the 14-variant build was 12 % slower.)
-template <int NPH, int S, bool NARROW, bool POOL, class AfterRows>
+// between carry zero weights and are not stored.
+//   part != nullptr : the RoI has several items -> bin-rows go, transposed, to part[(p*7 + pw)*32] (lane-major,
+//                     128-byte coalesced stores); the caller counts the item done afterwards
+//   else            : whole-RoI item -> pool tile + one bulk store if a tile is free, otherwise (and for ragged
+//                     groups / the cp.async variant) one bin-row [32 ch][7] at a time through `stage`
+template <int NPH, int S, bool POOL>
 __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
-                                         const int (&ooff)[kP], unsigned omask, float* __restrict__ pool, int* locks,
-                                         int warp, bool tile_out, int& held, AfterRows after_rows) {
-  constexpr int NX = NARROW ? kP : kP * S;
+                                         float* __restrict__ part, const int (&ooff)[kP], unsigned omask,
+                                         float* __restrict__ pool, int* locks, int warp, bool tile_out, int& held) {
+  constexpr int NX = kP * S;
   constexpr int RV = NPH > 2 ? 2 : 1;
+  constexpr bool PACK = S == 2;
   uint32_t xa[NX];
-  float lx[NX], hx[NX], mx[NARROW ? NX : 1];
-  if (NARROW) {
-#pragma unroll
-    for (int k = 0; k < NX; ++k) {
-      const float4 t = slot[1 + k];
-      xa[k] = lane_base + (uint32_t)__float_as_int(t.x);
-      hx[k] = t.y;
-      mx[k] = t.z;
-      lx[k] = t.w;
-    }
-  } else if (B2D_FFMA2 && S == 2) {
+  float lx[NX], hx[NX];
+  if (PACK) {
     // offsets only; the weights are read as pairs below
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -573,7 +513,6 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc2[p][j] = make_float2(0.0f, 0.0f);
 #define B2D_ACC(p, pw) (((pw) & 1) ? acc2[p][(pw) >> 1].y : acc2[p][(pw) >> 1].x)
-  constexpr bool PACK = B2D_FFMA2 && S == 2 && !NARROW;
   // x weights of the bin pairs (0,1), (2,3), (4,5): tap a, b of the first sample, c, d of the second
   float2 wa[PACK ? 3 : 1], wb[PACK ? 3 : 1], wc[PACK ? 3 : 1], wd[PACK ? 3 : 1];
   if (PACK) {
@@ -587,15 +526,11 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
     }
   }
 
-  constexpr int NT = NARROW ? 3 * kP : 2 * S * kP;      // taps per feature row
+  constexpr int NT = 2 * S * kP;      // taps per feature row
   auto load_row = [&](float (&t)[NT], uint32_t ro) {
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
-      if (NARROW) {
-        t[3 * pw] = lds_at(xa[pw] + ro);
-        t[3 * pw + 1] = lds_at(xa[pw] + ro + 4);
-        t[3 * pw + 2] = lds_at(xa[pw] + ro + 8);
-      } else if (S == 2) {
+      if (S == 2) {
         t[4 * pw] = lds_at(xa[2 * pw] + ro);
         t[4 * pw + 1] = lds_at(xa[2 * pw] + ro + 4);
         t[4 * pw + 2] = lds_at(xa[2 * pw + 1] + ro);
@@ -644,20 +579,8 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
     }
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
-      float v;
-      if (NARROW) {
-        v = hx[pw] * t[3 * pw];
-        v = fmaf(mx[pw], t[3 * pw + 1], v);
-        v = fmaf(lx[pw], t[3 * pw + 2], v);
-      } else if (S == 2) {
-        v = hx[2 * pw] * t[4 * pw];
-        v = fmaf(lx[2 * pw], t[4 * pw + 1], v);
-        v = fmaf(hx[2 * pw + 1], t[4 * pw + 2], v);
-        v = fmaf(lx[2 * pw + 1], t[4 * pw + 3], v);
-      } else {
-        v = hx[pw] * t[2 * pw];
-        v = fmaf(lx[pw], t[2 * pw + 1], v);
-      }
+      float v = hx[pw] * t[2 * pw];
+      v = fmaf(lx[pw], t[2 * pw + 1], v);
 #pragma unroll
       for (int p = 0; p < NPH; ++p) B2D_ACC(p, pw) = fmaf(wy[p], v, B2D_ACC(p, pw));
     }
@@ -666,46 +589,34 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
   // which lets the taps use [column + uniform row + imm] addressing.  Reading row entries past the last
   // row stays inside shared memory; such entries are never used as addresses.
   auto row_off = [](const float4& f0) { return __reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(f0.x)); };
-  constexpr int R1 = RV == 2 ? 1 : 0;
-  if (B2D_TAP_PIPE && NPH <= B2D_TAP_PIPE_MAX_NPH) {
-    // software pipeline: the taps of row i + 1 are in flight while row i is contracted (two register sets),
-    // row entries run two rows ahead so the LDS -> CREDUX -> tap-address chain is off the critical path
-    float ta[NT], tb[NT];
-    float4 a0 = slot[kRowVec0], a1 = slot[kRowVec0 + R1];
-    float4 b0 = slot[kRowVec0 + RV], b1 = slot[kRowVec0 + RV + R1];
-    load_row(ta, row_off(a0));
-    for (int i = 0; i < nrows; i += 2) {
-      const bool has_b = i + 1 < nrows;
-      const float4 c0 = slot[kRowVec0 + (i + 2) * RV], c1 = slot[kRowVec0 + (i + 2) * RV + R1];
-      if (has_b) load_row(tb, row_off(b0));
-      compute_row(ta, a0, a1);
-      if (!has_b) break;
-      const float4 d0 = slot[kRowVec0 + (i + 3) * RV], d1 = slot[kRowVec0 + (i + 3) * RV + R1];
-      if (i + 2 < nrows) load_row(ta, row_off(c0));
-      compute_row(tb, b0, b1);
-      a0 = c0;
-      a1 = c1;
-      b0 = d0;
-      b1 = d1;
-    }
-  } else {
-    // row entries are fetched one row ahead so that the LDS -> CREDUX -> tap-address chain of row i + 1
-    // overlaps the taps of row i
-    float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + R1];
-#pragma unroll kRowUnroll
-    for (int i = 0; i < nrows; ++i) {
-      const float4 f0 = e0, f1 = e1;
-      const uint32_t ro = row_off(f0);
-      e0 = slot[kRowVec0 + (i + 1) * RV];
-      if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
-      float t[NT];
-      load_row(t, ro);
-      compute_row(t, f0, f1);
-    }
+  // row entries are fetched one row ahead so that the LDS -> CREDUX -> tap-address chain of row i + 1
+  // overlaps the taps of row i
+  float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + (RV == 2 ? 1 : 0)];
+#pragma unroll 1
+  for (int i = 0; i < nrows; ++i) {
+    const float4 f0 = e0, f1 = e1;
+    const uint32_t ro = row_off(f0);
+    e0 = slot[kRowVec0 + (i + 1) * RV];
+    if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
+    float t[NT];
+    load_row(t, ro);
+    compute_row(t, f0, f1);
   }
-  after_rows();      // the ring is not needed any more: lets the caller release it early
-  if (POOL && NPH == kP && kPool > 0) {
-    if (tile_out && nph == kP) {
+#ifdef B2D_AB_NOSTORE
+  return;      // A/B timing build: results discarded
+#endif
+  if (POOL) {
+    if (part != nullptr) {
+      // one item of a split RoI: bin-rows transposed into the RoI's slice, 128 bytes per store
+#pragma unroll
+      for (int p = 0; p < NPH; ++p) {
+        if (p >= nph) break;
+#pragma unroll
+        for (int pw = 0; pw < kP; ++pw) part[(p * kP + pw) * kCh] = B2D_ACC(p, pw);
+      }
+      return;
+    }
+    if (NPH == kP && kPool > 0 && tile_out && nph == kP) {
       const int t = tile_try_acquire(locks, warp, lane);
       if (t >= 0) {
         float* tile = pool + (size_t)t * kTileWords;
@@ -721,19 +632,17 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
       }
     }
   }
-  // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw); two
-  // tiles alternate, so the shared-memory round trip of bin-row p overlaps the staging of p + 1
+  // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw)
 #pragma unroll
   for (int p = 0; p < NPH; ++p) {
     if (p >= nph) break;
-    float* tile = stage + (B2D_OUT_TILES > 1 ? (p & 1) * (kCh * kP) : 0);
-    if (B2D_OUT_TILES == 1 && p > 0) __syncwarp();
+    if (p > 0) __syncwarp();
 #pragma unroll
-    for (int pw = 0; pw < kP; ++pw) tile[lane * kP + pw] = B2D_ACC(p, pw);
+    for (int pw = 0; pw < kP; ++pw) stage[lane * kP + pw] = B2D_ACC(p, pw);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kP; ++j)
-      if (omask & (1u << j)) o[p * kP + ooff[j]] = tile[lane + 32 * j];
+      if (omask & (1u << j)) o[p * kP + ooff[j]] = stage[lane + 32 * j];
   }
   __syncwarp();
 #undef B2D_ACC
@@ -744,7 +653,7 @@ struct KArgs {
   RoiList L;
   int C, H, W;
   int lane_stride, row_words, stage_w;
-  int St, nblk, nbk, nsteps, items_cap, nostore;
+  int St, nblk, nbk, nsteps, items_cap, cnt_bytes;
   Ws ws;
   float* out;
 };
@@ -769,20 +678,20 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const int c0 = blockIdx.x * kCh;
   const int C = a.C, H = a.H, W = a.W;
   const int nch = min(kCh, C - c0);
-  const int split = gridDim.z, part = blockIdx.z;
+  const int part = blockIdx.z;
   constexpr int bins = kP * kP;
-  const int St = a.St, nblk = a.nblk, nbk = a.nbk, nsteps = a.nsteps;
-  const int nb = nsteps + 1;
+  const int St = a.St, nblk = a.nblk, nsteps = a.nsteps;
   const int row_words = a.row_words;
   const float* fbase = feat_g + ((size_t)f * C + c0) * H * W;
-  // dynamic shared: [ring (128-byte aligned)][record slots][staging tiles]
+  // dynamic shared: [ring (128-byte aligned)][record slots][bin-row tiles][pool][staging][counters]
   // (pointer arithmetic on `smem` keeps the shared address space; a cast through an integer would
   // turn every slot / staging access into a generic load)
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
   float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
-  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * B2D_OUT_TILES * kCh * kP;
-  float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * B2D_OUT_TILES * kCh * kP;
-  float* stg = pool + (size_t)kPool * kTileWords;
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * kCh * kP;
+  float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * kCh * kP;
+  float* stg = pool + (FILL ? (size_t)kPool * kTileWords : 0);
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(stg + (FILL ? (size_t)kStages * kCh * a.stage_w : 0));   // one byte per RoI of the frame
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
   if (tid < kPool) s_tile_lock[tid] = 0;
@@ -794,6 +703,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       mbar_init(&done_bar[i], kConsumers);
     }
   }
+  for (int i = tid; i < a.cnt_bytes / 4; i += kThreads) s_cnt[i] = 0u;
   {
     // pad columns x in [W, pitch) are read by clamped taps with weight 0: keep them finite
     const int pitch = a.lane_stride, padw = pitch - W;
@@ -807,10 +717,6 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   if (FILL && warp >= kConsumers) {
     // ---------------- producer: one tiled TMA per feature row (box = [32 planes][W]) into a dense
     // staging buffer, then repack the staged row into its skewed ring slot
-#ifdef B2D_ROWS_TIMING
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    DBG_T0(tp);
     const int Ws = a.stage_w;                                     // staged row width (>= W, multiple of 4)
     const uint32_t row_tx = (uint32_t)kCh * (uint32_t)Ws * 4u;    // the box is always 32 planes (OOB planes / elements zero-filled)
     const int nchunk = (W + 31) / 32;
@@ -828,34 +734,26 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     for (int y = 0; y < kStages && y < H; ++y) fetch(y);
     for (int y = 0; y < H; ++y) {
       const int b = y / St, dy = y - b * St;
-      {
-        DBG_T0(t1);
-        if (dy == 0 && b >= nblk) {
-          // the slot is free once every consumer warp works in a bucket beyond b - nblk
-          for (;;) {
-            int pr = lane < kConsumers ? *reinterpret_cast<volatile int*>(&s_progress[lane]) : 0x7fffffff;
-            pr = (int)__reduce_min_sync(0xffffffffu, (unsigned)pr);
-            if (pr > b - nblk) break;
-            __nanosleep(64);
-          }
+      if (dy == 0 && b >= nblk) {
+        // the slot is free once every consumer warp works in a bucket beyond b - nblk
+        for (;;) {
+          int pr = lane < kConsumers ? *reinterpret_cast<volatile int*>(&s_progress[lane]) : 0x7fffffff;
+          pr = (int)__reduce_min_sync(0xffffffffu, (unsigned)pr);
+          if (pr > b - nblk) break;
+          __nanosleep(64);
         }
-        DBG_ACC(5, t1);
       }
-      {
-        DBG_T0(t2);
-        mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
-        DBG_ACC(6, t2);
-      }
+      mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
       const uint32_t sstep = (uint32_t)Ws * 4u, dstep = (uint32_t)a.lane_stride * 4u;
-      uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * Ws) + (uint32_t)(lane + ((y * W) & 3)) * 4u +
-                     (uint32_t)(pw_id * kChP) * sstep;
-      uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
-                     (uint32_t)(pw_id * kChP) * dstep;
-      // batches of 8 channels x up to 4 chunks (32 values per lane); with B2D_REPACK_PIPE the loads of batch
-      // i + 1 are issued before the stores of batch i
+      const uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * Ws) + (uint32_t)(lane + ((y * W) & 3)) * 4u +
+                           (uint32_t)(pw_id * kChP) * sstep;
+      const uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
+                           (uint32_t)(pw_id * kChP) * dstep;
+      // batches of 8 channels x up to 4 chunks (32 values per lane)
       const int ncg = (nchunk + 3) / 4, nbat = (kChP / 8) * ncg;
-      auto bat_ld = [&](float (&v)[32], int bi) {
+      for (int bi = 0; bi < nbat; ++bi) {
         const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -864,9 +762,6 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
             if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j * 4 + k]) : "r"(src + (c8 + j) * sstep + 128u * ch) : "memory");
           }
-      };
-      auto bat_st = [&](const float (&v)[32], int bi) {
-        const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -875,39 +770,14 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
             if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
               asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (c8 + j) * dstep + 128u * ch), "f"(v[j * 4 + k]) : "memory");
           }
-      };
-      if (B2D_REPACK_PIPE) {
-        float va[32], vb[32];
-        bat_ld(va, 0);
-        for (int bi = 0; bi < nbat; bi += 2) {
-          if (bi + 1 < nbat) bat_ld(vb, bi + 1);
-          bat_st(va, bi);
-          if (bi + 2 < nbat) bat_ld(va, bi + 2);
-          if (bi + 1 < nbat) bat_st(vb, bi + 1);
-        }
-      } else {
-        float va[32];
-        for (int bi = 0; bi < nbat; ++bi) {
-          bat_ld(va, bi);
-          bat_st(va, bi);
-        }
       }
       __syncwarp();
       if (kProducers > 1) asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");   // all producers done with the buffer
-      {
-        DBG_T0(t4);
-        if (y + kStages < H) fetch(y + kStages);     // this staging buffer is free again
-        DBG_ACC(4, t4);
-      }
+      if (y + kStages < H) fetch(y + kStages);     // this staging buffer is free again
       if (dy == St - 1 || y == H - 1) {
         if (lane == 0) mbar_arrive(&full_bar[b % nblk]);
       }
     }
-    DBG_ACC(7, tp);
-#ifdef B2D_ROWS_TIMING
-    if (lane == 0)
-      for (int i = 4; i < 8; ++i) atomicAdd(&g_dbg[i], (unsigned long long)dbg_acc[i]);
-#endif
     return;
   }
 
@@ -922,20 +792,27 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     ooff[j] = idx + c * (bins - kP);
     if (c < nch) omask |= 1u << j;
   }
-  if (a.nostore) omask = 0u;
   const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)a.lane_stride * 4u;
   // bulk stores need 16-byte aligned RoI slices: C * 49 * 4 bytes per RoI -> C % 4 == 0
-  const bool tile_out = FILL && nch == kCh && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out_g) & 15u) == 0 && !a.nostore;
+  const bool tile_out = FILL && nch == kCh && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out_g) & 15u) == 0;
+#ifdef B2D_AB_NOSTORE
+  const bool parts_on = false;
+#else
+  const bool parts_on = tile_out && a.cnt_bytes > 0;    // split RoIs are assembled in their own output slice
+#endif
   int held = -1;        // pool tile a bulk store of this warp may still be reading
+  int pend_e = -1;      // split RoI whose item this warp has just stored (counted done at the next item)
+  int pend_r = 0, pend_n = 0;
   const float4* recs = records_g + (size_t)f * a.items_cap * kRecVec;
-  const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.bucket_start[(size_t)f * (nb + 2) + nb]);
+  const int item0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part]);
+  const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part + 1]);
 
-  // work claiming: item index = part + split * (shared counter)
+  // work claiming: item index = first item of this CTA's part + shared counter
   auto claim = [&]() -> int {
     unsigned v = 0;
     if (lane == 0) v = (unsigned)atomicAdd(&s_ctr, 1);
     v = __reduce_max_sync(0xffffffffu, v);        // broadcast that ptxas knows to be uniform
-    return part + split * (int)v;
+    return item0 + (int)v;
   };
 
   // cp.async fill, cooperative: block b may be written once every warp has released bucket b - nblk.
@@ -973,17 +850,11 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   };
   int cur = 0;          // buckets < cur are released by this warp
   int landed = 0;       // blocks < landed have been observed in the ring by this warp
-#ifdef B2D_ROWS_TIMING
-  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-  DBG_T0(tc);
   auto observe = [&](int upto) {
-    DBG_T0(t1);
     // the single producer arrives block after block, so block b landed implies all earlier ones; a
     // parity test is valid as long as the block one phase earlier (b - nblk) is known to have landed
     if (FILL && upto > landed && upto - 1 - nblk < landed) landed = upto - 1;
     for (; landed < upto; ++landed) wait_on(&full_bar[landed % nblk], (uint32_t)((landed / nblk) & 1));
-    DBG_ACC(1, t1);
   };
   // mbarrier parity waits are only meaningful within one phase of the barrier's current phase, so
   // every warp walks both barrier arrays strictly in order: it observes block j before it releases
@@ -1006,15 +877,53 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     }
     for (int j = cur; j < to; ++j) {
       observe(j + 1);
-      {
-        DBG_T0(t2);
-        if (j >= nblk) wait_on(&done_bar[j % nblk], (uint32_t)(((j - nblk) / nblk) & 1));
-        DBG_ACC(2, t2);
-      }
+      if (j >= nblk) wait_on(&done_bar[j % nblk], (uint32_t)(((j - nblk) / nblk) & 1));
       __syncwarp();
       if (lane == 0) mbar_arrive(&done_bar[j % nblk]);
     }
     cur = max(cur, to);
+  };
+  // Between items: give back the pool tile of the previous bulk store, then count the previous split item
+  // done; the warp that completes a RoI's count turns the assembled slice [49 bins][32 ch] (written by this
+  // CTA's warps, L2-resident) into the final [32 ch][49] layout, in place.
+  auto between_items = [&]() {
+    // (`held` / `pend_e` are warp-uniform; the reductions tell ptxas so - a branch it takes for divergent
+    // costs the consumers their [column + uniform row] tap addressing)
+    if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
+      // the bulk store issued by the previous item has (nearly always) read its tile by now
+      if (lane == 0) bulk_wait_read();
+      tile_release(s_tile_lock, held, lane);
+      held = -1;
+    }
+    if (FILL && __reduce_max_sync(0xffffffffu, (unsigned)(pend_e + 1)) != 0u) {
+      __threadfence();                          // this warp's part stores are performed before it is counted
+      __syncwarp();
+      unsigned old = 0u;
+      if (lane == 0) old = atomicAdd(&s_cnt[pend_e >> 2], 1u << (8 * (pend_e & 3)));
+      old = (__reduce_max_sync(0xffffffffu, old) >> (8 * (pend_e & 3))) & 0xFFu;
+      if ((int)old + 1 == pend_n) {
+        __threadfence();                        // acquire: every other item's stores are visible
+        float* slice = out_g + ((size_t)pend_r * C + c0) * bins;
+        float v[bins];
+#pragma unroll
+        for (int k = 0; k < bins; ++k) v[k] = __ldcg(slice + k * kCh + lane);
+        const int t = tile_try_acquire(s_tile_lock, warp, lane);
+        if (__reduce_max_sync(0xffffffffu, (unsigned)(t + 1)) != 0u) {
+          float* tile = pool + (size_t)t * kTileWords;
+#pragma unroll
+          for (int k = 0; k < bins; ++k) tile[lane * bins + k] = v[k];
+          asm volatile("fence.proxy.async;" ::: "memory");   // tile writes (shared) and the slice's earlier generic writes (global) before the bulk copy
+          __syncwarp();
+          if (lane == 0) bulk_s2g(slice, smem_u32(tile), (uint32_t)kTileWords * 4u);
+          held = t;
+        } else {
+          __syncwarp();                         // every lane has read the whole slice before any lane overwrites it
+#pragma unroll
+          for (int k = 0; k < bins; ++k) slice[lane * bins + k] = v[k];
+        }
+      }
+      pend_e = -1;
+    }
   };
   pump();
   int pending = claim();
@@ -1025,56 +934,39 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
 
   while (pending < n_items) {
     pump();
-    // (`held` is warp-uniform; the reduction tells ptxas so - a branch it takes for divergent costs the
-    // consumers their [column + uniform row] tap addressing)
-    if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
-      // the bulk store issued by the previous item has (nearly always) read its tile by now
-      if (lane == 0) bulk_wait_read();
-      tile_release(s_tile_lock, held, lane);
-      held = -1;
-    }
+    between_items();
     slot[lane] = rec_next;
     __syncwarp();
     const int nxt = claim();
     rec_next = __ldg(recs + (size_t)min(nxt, n_items - 1) * kRecVec + lane);
     const float4 hdr = slot[0];
     // header fields are warp-uniform; the reductions make that visible to ptxas (uniform branches / loops)
-    const int r = __float_as_int(hdr.x);
+    const int r = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.x));
     const int code = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.y));
-    const int bucket = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
+    const int blocks = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
+    const int ent = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.w));
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
+    const int bucket = blocks & 0xFFFF, last_blk = blocks >> 16;
+    const int roi_items = ent >> 24;
     float* o = out_g + ((size_t)r * C + c0) * bins + ph0 * kP;
+    // items of a split RoI store into the transposed slice and are counted
+    const bool is_part = parts_on && roi_items > 1;
+    float* part_dst = is_part ? out_g + ((size_t)r * C + c0) * bins + (size_t)ph0 * kP * kCh + lane : nullptr;
+    if (is_part) {
+      pend_e = ent & 0xFFFFFF;
+      pend_r = r;
+      pend_n = roi_items;
+    }
     if (!((code >> 16) & 1)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
+      // (only the blocks the item reads have to be there, not its whole window)
       release(bucket);
-      // only the blocks the item reads have to be there (B2D_OBSERVE_ALL: the whole window, as before)
-      const int last_blk = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.w));
-      observe(min(B2D_OBSERVE_ALL ? bucket + nbk : last_blk + 1, nsteps));
-      // once the rows of this item are done the warp only needs what its NEXT item needs (already
-      // claimed, record in flight since the top of the loop): publish that bucket before the output
-      // phase so the producer can refill while this warp stages and stores
-      auto early = [&]() {
-        if (!FILL || !B2D_EARLY) return;
-        const unsigned nb_next = __reduce_max_sync(0xffffffffu, lane == 0 ? (unsigned)__float_as_int(rec_next.z) : 0u);
-        release(nxt < n_items ? (int)nb_next : nsteps);
-      };
-      DBG_T0(t3);
-#define B2D_RUN(N, NAR) \
-  run_item<N, S, NAR, FILL>(slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held, early)
-      if (B2D_NARROW && S == 2 && ((code >> 17) & 1)) {
-        if (nph <= 2) B2D_RUN(2, true);
-        else if (nph <= 4) B2D_RUN(4, true);
-        else B2D_RUN(7, true);
-      } else {
-        if (nph <= 2) B2D_RUN(2, false);
-        else if (nph <= 4) B2D_RUN(4, false);
-        else B2D_RUN(7, false);
-      }
+      observe(min(last_blk + 1, nsteps));
+#define B2D_RUN(N) run_item<N, S, FILL>(slot, nrows, nph, lane_base, stage, lane, o, part_dst, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
+      if (nph <= 2) B2D_RUN(2);
+      else if (nph <= 4) B2D_RUN(4);
+      else B2D_RUN(7);
 #undef B2D_RUN
-      DBG_ACC(3, t3);
-#ifdef B2D_ROWS_TIMING
-      dbg_acc[4] += 0;
-#endif
     } else {
       // bin-row taller than the resident window: taps straight from global memory (rare)
       const bool ch_ok = lane < nch;
@@ -1094,19 +986,18 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
             acc += ty.wlo * top + ty.whi * bot;
           }
         }
-        if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
+#ifndef B2D_AB_NOSTORE
+        if (is_part) part_dst[pw * kCh] = acc / g.count;
+        else if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
+#endif
       }
     }
     __syncwarp();
     pending = nxt;
   }
   // out of items: release every remaining bucket so the fill can finish
-  DBG_ACC(0, tc);
-#ifdef B2D_ROWS_TIMING
-  if (lane == 0)
-    for (int i = 0; i < 5; ++i) atomicAdd(&g_dbg[i], (unsigned long long)dbg_acc[i]);
-#endif
   release(nsteps);
+  between_items();      // count the last split item (and possibly assemble its RoI)
   if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {   // the last bulk store still reads shared memory
     if (lane == 0) bulk_wait_read();
     tile_release(s_tile_lock, held, lane);
@@ -1148,32 +1039,20 @@ static bool make_tmap(CUtensorMap* map, const float* feat, int F, int C, int H, 
 
 }  // namespace rows
 
-#ifdef B2D_ROWS_TIMING
-extern "C" void b2d_rows_debug(unsigned long long* out8, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, rows::g_dbg, sizeof(unsigned long long) * 8);
-  if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaMemcpyToSymbol(rows::g_dbg, z, sizeof(z));
-  }
-}
-#endif
-
-size_t rows_workspace_bytes(int F, int H, int per_frame) { return rows::carve(nullptr, F, per_frame, H).bytes; }
+size_t rows_workspace_bytes(int F, int /*H*/, int per_frame) { return rows::carve(nullptr, F, per_frame).bytes; }
 
 // Returns B2D_ERR_UNSUPPORTED when this path does not apply (caller falls back).
 int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const RoiList& L, int PH, int PW,
-                           float scale, int S, int aligned, float* out, void* workspace, size_t workspace_bytes,
-                           cudaStream_t st) {
+                           float scale, int S, int aligned, bool coop_fill, float* out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
   using namespace rows;
-  if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 27)) return B2D_ERR_UNSUPPORTED;
-  const bool coop = getenv("B2D_ROWS_COOP_FILL") != nullptr;   // test knob: force the cp.async fill
+  if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 24)) return B2D_ERR_UNSUPPORTED;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  const Plan p = make_plan(H, W, !coop && make_tmap(&tmap, feat, F, C, H, W));
-  if (!p.ok) return B2D_ERR_UNSUPPORTED;
   const int per_frame = L.seg_count ? L.seg_stride : L.n;
-  Ws ws = carve(workspace, F, per_frame, H);
+  const Plan p = make_plan(H, W, per_frame, !coop_fill && make_tmap(&tmap, feat, F, C, H, W));
+  if (!p.ok || p.nsteps >= 0xFFFF) return B2D_ERR_UNSUPPORTED;
+  Ws ws = carve(workspace, F, per_frame);
   if (!workspace || workspace_bytes < ws.bytes) return B2D_ERR_UNSUPPORTED;
   ws.scale = scale;
   ws.aligned = aligned;
@@ -1185,14 +1064,14 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   }
   const int groups = ceil_div(C, kCh) * F;
   int split = 1;
-  while (split < 4 && groups * split < 2 * kNumSMs) split *= 2;
+  while (split < kMaxSplit && groups * split < 2 * kNumSMs) split *= 2;
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
-  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, getenv("B2D_NOSTORE") ? 1 : 0, ws, out};
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, p.cnt_bytes, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * nb, st>>>(L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole,   \
-                                                          p.nsteps, p.row_words * 4, items_cap, ws);              \
+    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * split * nb, st>>>(                        \
+        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, items_cap, split, ws); \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
     fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap, feat, ws.records, L.rois, out);                    \

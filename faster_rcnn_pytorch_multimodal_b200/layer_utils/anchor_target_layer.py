@@ -35,7 +35,7 @@ def anchor_target_layer_torch(gt_boxes, gt_boxes_dc, info, all_anchors, num_anch
         pad = torch.zeros(1, 7, device=device)
         pad[:, :info_t.shape[1]] = info_t
         info_t = pad
-    L = lib()
+    L = lib(device)
     ws = workspaces.get(device, "anchor_target", L.b2d_anchor_target_workspace_bytes(1, N, G))
     num_gt = torch.tensor([G], dtype=torch.int32, device=device)
     counts = torch.empty(1, 4, dtype=torch.int32, device=device)

@@ -61,7 +61,7 @@ def proposal_target_layer(rpn_rois, rpn_scores, anchors_3d, gt_boxes, true_gt_bo
     fg_list = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
     bg_list = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
     counts = torch.empty(2, dtype=torch.int32, device=dev)
-    L, st = lib(), stream_ptr(dev)
+    L, st = lib(dev), stream_ptr(dev)
     bg_mode = 0 if cfg.TRAIN.get('BG_MODE', 'strict') == 'strict' else 1
     check(L.b2d_proposal_target_phase1(R, G, ptr(rois), ptr(gt), float(cfg.TRAIN.FG_THRESH),
                                        float(cfg.TRAIN.BG_THRESH_HI), float(cfg.TRAIN.BG_THRESH_LO), bg_mode,

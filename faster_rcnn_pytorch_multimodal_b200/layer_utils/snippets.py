@@ -21,7 +21,7 @@ def generate_anchors_pre(height, width, feat_stride, anchor_scales=(8, 16, 32), 
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     out = torch.empty(int(height) * int(width) * A, 4, device=device)
     flat = np.ascontiguousarray(base.reshape(-1), dtype=np.float64)
-    check(lib().b2d_generate_anchors(int(height), int(width), int(feat_stride), A,
+    check(lib(device).b2d_generate_anchors(int(height), int(width), int(feat_stride), A,
                                      flat.ctypes.data_as(C.POINTER(C.c_double)), ptr(out), stream_ptr(device)),
           "b2d_generate_anchors")
     return out, np.int32(out.shape[0])

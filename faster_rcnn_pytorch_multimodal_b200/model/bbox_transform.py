@@ -25,7 +25,7 @@ def bbox_transform(ex_rois, gt_rois):
     ex, gt = f32c(ex_rois), f32c(gt_rois)
     n = ex.shape[0]
     out = torch.empty(n, 4, device=ex.device)
-    check(lib().b2d_bbox_transform(n, ptr(ex), ex.stride(0) if n else 4, ptr(gt), gt.stride(0) if n else 4, ptr(out),
+    check(lib(ex.device).b2d_bbox_transform(n, ptr(ex), ex.stride(0) if n else 4, ptr(gt), gt.stride(0) if n else 4, ptr(out),
                                    stream_ptr(ex.device)), "b2d_bbox_transform")
     return out
 
@@ -40,7 +40,7 @@ def bbox_transform_inv(boxes, deltas, scales=None):
     k = d.shape[1] // 4
     out = torch.empty(n, 4 * k, device=b.device)
     use_scale = scales is not None
-    check(lib().b2d_bbox_transform_inv(n, k, ptr(b), b.stride(0), ptr(d), int(use_scale),
+    check(lib(b.device).b2d_bbox_transform_inv(n, k, ptr(b), b.stride(0), ptr(d), int(use_scale),
                                        float(scales) if use_scale else 1.0, 0, None, ptr(out),
                                        stream_ptr(b.device)), "b2d_bbox_transform_inv")
     return out
@@ -55,7 +55,7 @@ def clip_boxes(boxes, shape):
     out = torch.empty_like(b)
     if n:
         info = _info_dev(shape, b.device)
-        check(lib().b2d_clip_boxes(n, k, ptr(b), ptr(info), ptr(out), stream_ptr(b.device)), "b2d_clip_boxes")
+        check(lib(b.device).b2d_clip_boxes(n, k, ptr(b), ptr(info), ptr(out), stream_ptr(b.device)), "b2d_clip_boxes")
     return out.view(n, -1)
 
 
@@ -65,7 +65,7 @@ def lidar_3d_bbox_transform(ex_rois, ex_anchors, gt_rois):
     r, a, g = f32c(ex_rois), f32c(ex_anchors), f32c(gt_rois)
     n = r.shape[0]
     out = torch.empty(n, 7, device=r.device)
-    check(lib().b2d_lidar_bbox_transform(n, ptr(r), r.stride(0) if n else 4, ptr(a), ptr(g),
+    check(lib(r.device).b2d_lidar_bbox_transform(n, ptr(r), r.stride(0) if n else 4, ptr(a), ptr(g),
                                          g.stride(0) if n else 7, ptr(out), stream_ptr(r.device)),
           "b2d_lidar_bbox_transform")
     return out
@@ -82,7 +82,7 @@ def _lidar_inv(rois, boxes, deltas, scales, mode):
     n = b.shape[0]
     k = d.shape[1] // 7
     out = torch.empty(n, 7 * k, device=b.device)
-    check(lib().b2d_lidar_bbox_transform_inv(n, k, ptr(r), r.stride(0) if n else 4, ptr(b), ptr(d), mode, ptr(out),
+    check(lib(b.device).b2d_lidar_bbox_transform_inv(n, k, ptr(r), r.stride(0) if n else 4, ptr(b), ptr(d), mode, ptr(out),
                                              stream_ptr(b.device)), "b2d_lidar_bbox_transform_inv")
     return out
 

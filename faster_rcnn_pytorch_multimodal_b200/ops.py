@@ -47,7 +47,7 @@ def proposal_batched(cls_prob: torch.Tensor, bbox_pred: torch.Tensor, info: torc
         a3d_out = torch.empty(F, M, 7, device=dev)
     aidx = torch.empty(F, M, dtype=torch.int32, device=dev) if want_anchor_index else None
     num_out = torch.empty(F, dtype=torch.int32, device=dev)
-    L = lib()
+    L = lib(dev)
     nbytes = L.b2d_proposal_workspace_bytes(F, n_loc, A, pre_nms, post_nms)
     ws = workspaces.get(dev, "proposal", nbytes)
     check(L.b2d_proposal(F, n_loc, A, ptr(cls_prob), ptr(bbox_pred), ptr(info), ptr(anchors), ptr(anchors_3d),
@@ -64,7 +64,7 @@ def proposal_sorted_debug(F, n_loc, A, pre_nms, post_nms, device):
     boxes = torch.empty(F, k, 4, device=device)
     scores = torch.empty(F, k, device=device)
     index = torch.empty(F, k, dtype=torch.int32, device=device)
-    L = lib()
+    L = lib(device)
     ws = workspaces.get(device, "proposal", L.b2d_proposal_workspace_bytes(F, n_loc, A, pre_nms, post_nms))
     check(L.b2d_proposal_debug_sorted(F, n_loc, A, pre_nms, post_nms, ptr(ws), ptr(boxes), ptr(scores), ptr(index),
                                       stream_ptr(device)), "b2d_proposal_debug_sorted")
@@ -84,7 +84,7 @@ def proposal_top_batched(cls_prob, bbox_pred, info, anchors, num_anchors, top_n,
     rois = torch.empty(F, top_n, 5, device=dev)
     scores = torch.empty(F, top_n, device=dev)
     anc = torch.empty(F, top_n, 4, device=dev)
-    L = lib()
+    L = lib(dev)
     nbytes = L.b2d_proposal_workspace_bytes(F, n_loc, A, top_n, top_n)
     ws = workspaces.get(dev, "proposal", nbytes)
     check(L.b2d_proposal_top(F, n_loc, A, ptr(cls_prob), ptr(bbox_pred), ptr(info7), ptr(anchors), int(top_n),
@@ -100,13 +100,13 @@ def nms_sorted(boxes: torch.Tensor, thresh: float, max_keep: int = -1,
                n_valid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """boxes [F,n,4] already in descending score order -> (keep [F,max_keep] int32, num_keep [F] int32)."""
     require_cuda(boxes, n_valid)
-    boxes = f32c(boxes)
+    boxes, n_valid = f32c(boxes), _lib.i32c(n_valid, "n_valid")
     F, n = boxes.shape[0], boxes.shape[1]
     mk = n if max_keep <= 0 else min(max_keep, n)
     keep = torch.empty(F, max(mk, 1), dtype=torch.int32, device=boxes.device)
     num = torch.zeros(F, dtype=torch.int32, device=boxes.device)
     if n > 0:
-        check(lib().b2d_nms_sorted(F, n, ptr(boxes), ptr(n_valid), float(thresh), mk, ptr(keep), ptr(num),
+        check(lib(boxes.device).b2d_nms_sorted(F, n, ptr(boxes), ptr(n_valid), float(thresh), mk, ptr(keep), ptr(num),
                                    stream_ptr(boxes.device)), "b2d_nms_sorted")
     return keep, num
 
@@ -118,7 +118,7 @@ def argsort_desc(scores: torch.Tensor) -> torch.Tensor:
     F, n = scores.shape
     order = torch.empty(F, n, dtype=torch.int32, device=scores.device)
     if n > 0:
-        check(lib().b2d_argsort_desc(F, n, ptr(scores), ptr(order), stream_ptr(scores.device)), "b2d_argsort_desc")
+        check(lib(scores.device).b2d_argsort_desc(F, n, ptr(scores), ptr(order), stream_ptr(scores.device)), "b2d_argsort_desc")
     return order
 
 
@@ -141,8 +141,14 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
 # ------------------------------------------------------------------------------------------
 # RoIAlign (torchvision.ops.roi_align drop-in, with autograd)
 # ------------------------------------------------------------------------------------------
+# kernel family of RoIAlign forward (include/b2d_glue.h b2d_roi_route); parity tests pin it, production leaves AUTO
+ROI_ROUTES = {"auto": 0, "rows": 1, "rows_coop": 2, "planes": 3, "gather": 4}
+ROI_ROUTE = "auto"
+
+
 def _roi_align_forward(feat, rois, out_hw, scale, sampling_ratio, aligned, roi_ids=None, seg_count=None,
-                       seg_stride=0, out=None):
+                       seg_stride=0, out=None, route=None):
+    roi_ids, seg_count = _lib.i32c(roi_ids, "roi_ids"), _lib.i32c(seg_count, "seg_count")
     Fr, Cc, H, W = feat.shape
     R = rois.shape[0]
     if out is None:
@@ -152,19 +158,20 @@ def _roi_align_forward(feat, rois, out_hw, scale, sampling_ratio, aligned, roi_i
     if R == 0 or (roi_ids is not None and roi_ids.numel() == 0):
         return out
     n_ids = 0 if roi_ids is None else roi_ids.numel()
-    L = lib()
+    L = lib(feat.device)
     n_list = n_ids if roi_ids is not None else R
     per_frame = int(seg_stride) if seg_count is not None else n_list
     ws = workspaces.get(feat.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, n_list, per_frame))
-    check(L.b2d_roi_align_forward(Fr, Cc, H, W, ptr(feat), ptr(rois), R, ptr(roi_ids), n_ids, ptr(seg_count),
-                                  int(seg_stride), out_hw[0], out_hw[1], float(scale), int(sampling_ratio),
-                                  int(bool(aligned)), ptr(out), ptr(ws), ws.numel(), stream_ptr(feat.device)),
-          "b2d_roi_align_forward")
+    check(L.b2d_roi_align_forward_route(Fr, Cc, H, W, ptr(feat), ptr(rois), R, ptr(roi_ids), n_ids, ptr(seg_count),
+                                        int(seg_stride), out_hw[0], out_hw[1], float(scale), int(sampling_ratio),
+                                        int(bool(aligned)), ROI_ROUTES[route or ROI_ROUTE], ptr(out), ptr(ws),
+                                        ws.numel(), stream_ptr(feat.device)), "b2d_roi_align_forward")
     return out
 
 
 def _roi_align_backward(grad_out, rois, feat_shape, out_hw, scale, sampling_ratio, aligned, roi_ids=None,
                         seg_count=None, seg_stride=0, grad_feat=None):
+    roi_ids, seg_count = _lib.i32c(roi_ids, "roi_ids"), _lib.i32c(seg_count, "seg_count")
     Fr, Cc, H, W = feat_shape
     accumulate = grad_feat is not None
     if grad_feat is None:
@@ -172,7 +179,7 @@ def _roi_align_backward(grad_out, rois, feat_shape, out_hw, scale, sampling_rati
     if rois.shape[0] == 0 or (roi_ids is not None and roi_ids.numel() == 0):
         return grad_feat if accumulate else grad_feat.zero_()
     n_ids = 0 if roi_ids is None else roi_ids.numel()
-    L = lib()
+    L = lib(grad_out.device)
     n_list = n_ids if roi_ids is not None else rois.shape[0]
     per_frame = int(seg_stride) if seg_count is not None else n_list
     ws = workspaces.get(grad_out.device, "roi_align", L.b2d_roi_align_workspace_bytes(Fr, Cc, H, W, n_list, per_frame))
@@ -212,8 +219,10 @@ def roi_align(input: torch.Tensor, boxes, output_size, spatial_scale: float = 1.
     if isinstance(boxes, (list, tuple)):
         boxes = torch.cat([torch.cat((b.new_full((b.shape[0], 1), float(i)), b), dim=1)
                            for i, b in enumerate(boxes)], dim=0)
-    return _RoIAlignFn.apply(input, boxes, int(output_size[0]), int(output_size[1]), float(spatial_scale),
-                             int(sampling_ratio), bool(aligned), seg_count, int(seg_stride))
+    out = _RoIAlignFn.apply(input, boxes, int(output_size[0]), int(output_size[1]), float(spatial_scale),
+                            int(sampling_ratio), bool(aligned), seg_count, int(seg_stride))
+    # the kernels compute in fp32; like torchvision the result comes back in the input's dtype (half / AMP features)
+    return out if out.dtype == input.dtype else out.to(input.dtype)
 
 
 class RoIAlign(torch.nn.Module):
@@ -235,7 +244,7 @@ def roi_align_forward_levels(feats, scales, rois, levels_i32, out_hw, sampling_r
     import ctypes as C
     require_cuda(rois, levels_i32, *feats)
     feats = [f32c(f) for f in feats]
-    rois = f32c(rois)
+    rois, levels_i32 = f32c(rois), _lib.i32c(levels_i32, "levels")
     n = len(feats)
     Fr, Cc = feats[0].shape[:2]
     R = rois.shape[0]
@@ -244,7 +253,7 @@ def roi_align_forward_levels(feats, scales, rois, levels_i32, out_hw, sampling_r
     hh = (C.c_int32 * n)(*[f.shape[2] for f in feats])
     ww = (C.c_int32 * n)(*[f.shape[3] for f in feats])
     sc = (C.c_float * n)(*[float(s) for s in scales])
-    check(lib().b2d_roi_align_forward_levels(n, Fr, Cc, fp, hh, ww, sc, ptr(rois), ptr(levels_i32), R, out_hw[0], out_hw[1],
+    check(lib(rois.device).b2d_roi_align_forward_levels(n, Fr, Cc, fp, hh, ww, sc, ptr(rois), ptr(levels_i32), R, out_hw[0], out_hw[1],
                                              int(sampling_ratio), int(bool(aligned)), ptr(out), stream_ptr(rois.device)),
           "b2d_roi_align_forward_levels")
     return out
@@ -256,7 +265,7 @@ def fpn_level_map(boxes: torch.Tensor, k_min: int, k_max: int, canonical_scale: 
     require_cuda(boxes)
     boxes = f32c(boxes)
     out = torch.empty(boxes.shape[0], dtype=torch.int32, device=boxes.device)
-    check(lib().b2d_fpn_level_map(boxes.shape[0], ptr(boxes), int(k_min), int(k_max), float(canonical_scale),
+    check(lib(boxes.device).b2d_fpn_level_map(boxes.shape[0], ptr(boxes), int(k_min), int(k_max), float(canonical_scale),
                                   int(canonical_level), float(eps), ptr(out), stream_ptr(boxes.device)),
           "b2d_fpn_level_map")
     return out if as_int32 else out.long()
@@ -300,7 +309,7 @@ def final_detections(cls_score, pred_boxes, info, num_elem, db_type, score_thres
     o_ur = torch.zeros(F, K, mo, n_ur, device=dev) if n_ur else None
     o_uc = torch.zeros(F, K, mo, n_uc * E, device=dev) if n_uc else None
     nr = num_rois.to(torch.int32).contiguous() if num_rois is not None else None
-    check(lib().b2d_final_detections(F, R, K, E, ptr(sc), ptr(pb), ptr(nr), ptr(inf), modes[db_type],
+    check(lib(dev).b2d_final_detections(F, R, K, E, ptr(sc), ptr(pb), ptr(nr), ptr(inf), modes[db_type],
                                      float(score_thresh), float(nms_thresh), int(max_dets), mo, ptr(ur), n_ur,
                                      ptr(ucl), n_uc, ptr(dets), ptr(det_roi), ptr(o_ur), ptr(o_uc), ptr(counts),
                                      stream_ptr(dev)), "b2d_final_detections")

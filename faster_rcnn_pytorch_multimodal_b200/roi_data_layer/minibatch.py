@@ -49,9 +49,9 @@ def lidar_bev_map(source_bin, scale=1.0, return_num_voxels=False):
     dev = pts.device
     out = torch.empty(ny, nx, nz + n_meta, device=dev)
     nvox = torch.empty(1, dtype=torch.int32, device=dev)
-    nbytes = lib().b2d_bev_workspace_bytes(max(n, 1), nx, ny, nz)
+    nbytes = lib(dev).b2d_bev_workspace_bytes(max(n, 1), nx, ny, nz)
     ws = workspaces.get(dev, "bev", nbytes)
-    check(lib().b2d_bev_rasterize(n, pts.shape[1], ptr(pts), L.X_RANGE[0], L.X_RANGE[1], L.Y_RANGE[0], L.Y_RANGE[1],
+    check(lib(dev).b2d_bev_rasterize(n, pts.shape[1], ptr(pts), L.X_RANGE[0], L.X_RANGE[1], L.Y_RANGE[0], L.Y_RANGE[1],
                                   L.Z_RANGE[0], L.Z_RANGE[1], voxel_len, L.VOXEL_HEIGHT, nx, ny, nz,
                                   int(L.MAX_PTS_PER_VOXEL), int(L.MAX_NUM_VOXEL), n_meta, elong, ptr(out), ptr(nvox),
                                   ptr(ws), ws.numel(), stream_ptr(dev)), "b2d_bev_rasterize")

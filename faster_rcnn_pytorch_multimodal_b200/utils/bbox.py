@@ -16,7 +16,7 @@ def bbox_overlaps(boxes, query_boxes):
     b, q = f32c(boxes), f32c(query_boxes)
     n, k = b.shape[0], q.shape[0]
     out = torch.empty(n, k, device=b.device)
-    check(lib().b2d_bbox_overlaps(n, k, ptr(b), b.stride(0) if n else 4, ptr(q), q.stride(0) if k else 4, ptr(out),
+    check(lib(b.device).b2d_bbox_overlaps(n, k, ptr(b), b.stride(0) if n else 4, ptr(q), q.stride(0) if k else 4, ptr(out),
                                   stream_ptr(b.device)), "b2d_bbox_overlaps")
     return out.cpu().numpy() if as_np else out
 
@@ -27,7 +27,7 @@ def bbaa_graphics_gems_torch(bboxes, width, height, clip=True):
     b = f32c(bboxes)
     n = b.shape[0]
     out = torch.empty(n, 4, device=b.device)
-    check(lib().b2d_bbaa(n, ptr(b), int(bool(clip)), float(width), float(height), ptr(out), stream_ptr(b.device)),
+    check(lib(b.device).b2d_bbaa(n, ptr(b), int(bool(clip)), float(width), float(height), ptr(out), stream_ptr(b.device)),
           "b2d_bbaa")
     return out
 

@@ -11,7 +11,7 @@ def _variance(bbox_samples, mode):
     T = x.shape[0]
     m = x[0].numel()
     out = torch.empty(x.shape[1:], device=x.device)
-    check(lib().b2d_mc_variance(T, m, ptr(x), mode, ptr(out), stream_ptr(x.device)), "b2d_mc_variance")
+    check(lib(x.device).b2d_mc_variance(T, m, ptr(x), mode, ptr(out), stream_ptr(x.device)), "b2d_mc_variance")
     return out
 
 
@@ -31,7 +31,7 @@ def _class_uncertainty(cls_score, want_mi, want_ent):
     T, n, K = z.shape
     mi = torch.empty(n, device=z.device) if want_mi else None
     ent = torch.empty(n, device=z.device) if want_ent else None
-    check(lib().b2d_mc_class_uncertainty(T, n, K, ptr(z), ptr(mi), ptr(ent), stream_ptr(z.device)),
+    check(lib(z.device).b2d_mc_class_uncertainty(T, n, K, ptr(z), ptr(mi), ptr(ent), stream_ptr(z.device)),
           "b2d_mc_class_uncertainty")
     return mi, ent
 
@@ -59,6 +59,6 @@ def sort_by_bbox_variance(var, descending=False):
     n, cols = v.shape
     key = torch.empty(n, device=v.device)
     order = torch.empty(n, dtype=torch.int32, device=v.device)
-    check(lib().b2d_var_sort(n, cols, ptr(v), int(bool(descending)), ptr(key), ptr(order), stream_ptr(v.device)),
+    check(lib(v.device).b2d_var_sort(n, cols, ptr(v), int(bool(descending)), ptr(key), ptr(order), stream_ptr(v.device)),
           "b2d_var_sort")
     return order.long(), key

@@ -90,7 +90,7 @@ class _MultiLevelFn(torch.autograd.Function):
         out = torch.zeros((R, C) + tuple(out_hw), device=feats[0].device)
         id_lists = []
         for lvl, (f, s) in enumerate(zip(feats, scales)):
-            ids = (levels == lvl).nonzero().view(-1).to(torch.int32).contiguous()   # device-side, no sync
+            ids = (levels == lvl).nonzero().view(-1).to(torch.int32).contiguous()   # device-side (nonzero() syncs the host for the count)
             id_lists.append(ids)
             ops._roi_align_forward(ops.f32c(f), rois_c, out_hw, s, sampling_ratio, False, roi_ids=ids, out=out)
         ctx.save_for_backward(rois_c, *id_lists)

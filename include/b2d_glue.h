@@ -16,7 +16,10 @@
  *    buffer, including `workspace` (size from the matching *_workspace_bytes()).
  *  - Return value: 0 on success, negative b2d_status otherwise.  Nothing throws.
  *  - Re-entrant; concurrent calls are safe on distinct streams + workspaces.
- *  - Every function takes a leading `num_frames`; frames are independent.
+ *  - The batched stages (proposal, NMS, RoIAlign, anchor targets, final detections, the host
+ *    pipeline) take a leading `num_frames`; frames are independent.  The element-wise codecs,
+ *    the RoI sampler, the MC reductions and the BEV rasteriser take a flat row count: stack the
+ *    rows of several frames to batch them.
  */
 #ifndef B2D_GLUE_H_
 #define B2D_GLUE_H_
@@ -119,7 +122,8 @@ int b2d_argsort_desc(int num_frames, int n, const float* scores, int32_t* order,
  *     else the list is rows 0..R-1;
  *   seg_count [F] int32 or NULL with seg_stride: frame f owns list entries
  *     [f*seg_stride, f*seg_stride + seg_count[f]) (the padded layout b2d_proposal() emits);
- *     entries past seg_count[f] produce zero rows.  When NULL every frame filters the list by col0.
+ *     entries past seg_count[f] produce zero rows.  When NULL every frame filters the list by col0
+ *     (rows whose col0 is outside [0,F) come back as zeros).
  *   out  [R, C, PH, PW]; grad_out same shape; grad_feat [F, C, H, W] (fully overwritten
  *   unless accumulate != 0).
  * Backward is deterministic and uses no atomics.
@@ -132,6 +136,22 @@ int b2d_roi_align_forward(int num_frames, int channels, int height, int width,
                           const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
                           int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
                           float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Same call with the kernel family pinned (parity tests cover every family on small shapes that the
+ * automatic dispatch would send elsewhere): AUTO = what b2d_roi_align_forward does; ROWS = streaming
+ * kernels, never the small-call gather; ROWS_COOP = rows kernel with its cp.async fill; PLANES = plane
+ * resident kernel; GATHER = one thread per output. */
+typedef enum b2d_roi_route {
+  B2D_ROI_ROUTE_AUTO = 0,
+  B2D_ROI_ROUTE_ROWS = 1,
+  B2D_ROI_ROUTE_ROWS_COOP = 2,
+  B2D_ROI_ROUTE_PLANES = 3,
+  B2D_ROI_ROUTE_GATHER = 4
+} b2d_roi_route;
+int b2d_roi_align_forward_route(int num_frames, int channels, int height, int width,
+                                const float* feat, const float* rois, int num_rois,
+                                const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,
+                                int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                                int route, float* out, void* workspace, size_t workspace_bytes, void* stream);
 int b2d_roi_align_backward(int num_frames, int channels, int height, int width,
                            const float* grad_out, const float* rois, int num_rois,
                            const int32_t* roi_ids, int n_roi_ids, const int32_t* seg_count, int seg_stride,

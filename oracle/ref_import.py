@@ -10,11 +10,17 @@ import os
 import sys
 import types
 
-REF_LIB = "/root/reference/lib"
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "lib")     # oracle/stage_ref.py
+REF_LIB = "/root/reference/lib" if os.path.isdir("/root/reference/lib") else _STAGED
 
 
 def available() -> bool:
-    return os.path.isdir(REF_LIB)
+    """The hot-path modules can be imported (build container: /root/reference; GPU box: the staged copy)."""
+    return os.path.isfile(os.path.join(REF_LIB, "layer_utils", "proposal_layer.py"))
+
+
+def source() -> str:
+    return "reference" if REF_LIB != _STAGED else "staged copy of the reference (oracle/_ref)"
 
 
 def _install_stubs():
@@ -59,7 +65,8 @@ def _install_stubs():
 def load():
     """Return a namespace of the reference's hot-path modules."""
     if not available():
-        raise RuntimeError("/root/reference is not present (expected on the GPU box)")
+        raise RuntimeError("neither /root/reference nor oracle/_ref is present (run `python -m oracle.stage_ref` in "
+                           "the build container)")
     _install_stubs()
     if REF_LIB not in sys.path:
         sys.path.insert(0, REF_LIB)
@@ -91,8 +98,8 @@ def load_minibatch():
     they are stubbed with empty modules.  ``spconv`` (pinned 1.0, ``req.txt:261``, not installable) is
     stubbed with the restatement in ``oracle/bev_oracle.py`` - the ONE piece of arithmetic on this path
     that therefore stays unpinned."""
-    if not available():
-        raise RuntimeError("/root/reference is not present (expected on the GPU box)")
+    if not os.path.isdir("/root/reference/lib/roi_data_layer"):
+        raise RuntimeError("/root/reference is not present (the data layer is not staged for the GPU box)")
     _install_stubs()
     if REF_LIB not in sys.path:
         sys.path.insert(0, REF_LIB)

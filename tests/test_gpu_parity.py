@@ -26,7 +26,8 @@ def _streaming_roi_kernels(request, monkeypatch):
     small too, so the suite pins them to the streaming kernels (rows / sweep / planes) they are meant to cover.
     Tests marked `sparse_path` run with the production dispatch."""
     if "sparse_path" not in request.keywords:
-        monkeypatch.setenv("B2D_ROI_NO_GATHER", "1")
+        from faster_rcnn_pytorch_multimodal_b200 import ops
+        monkeypatch.setattr(ops, "ROI_ROUTE", "rows")
 
 
 def T(a, d=None):
@@ -417,7 +418,7 @@ def test_roi_align_rows_kernel_waymo_shape(coop, sr, monkeypatch):
     """The streaming 'rows' kernel at the BASELINE feature-map size (80x120 ring, TMA and cp.async fills)."""
     from faster_rcnn_pytorch_multimodal_b200 import ops
     if coop:
-        monkeypatch.setenv("B2D_ROWS_COOP_FILL", "1")
+        monkeypatch.setattr(ops, "ROI_ROUTE", "rows_coop")
     F, C, H, W, M = 2, 64, 80, 120, 300
     g = torch.Generator().manual_seed(11)
     feat = torch.randn(F, C, H, W, generator=g)
@@ -509,7 +510,7 @@ def test_fpn_level_map_and_multiscale(golden, fused, monkeypatch):
     from faster_rcnn_pytorch_multimodal_b200.utils.torchpoolers import MultiScaleRoIAlign
     if not fused:
         monkeypatch.setattr(torchpoolers, "_FUSED_MAX_OUTPUTS", 0)
-        monkeypatch.setenv("B2D_ROI_NO_GATHER", "1")
+        monkeypatch.setattr(ops, "ROI_ROUTE", "rows")
     g = golden("thirdparty")
     fb = T(g["fpn_boxes"])
     assert torch.equal(ops.fpn_level_map(fb, 2, 5).cpu(), torch.from_numpy(g["fpn_levels"]))
