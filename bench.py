@@ -1,16 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: proposal + NMS + RoI-crop frames/s (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU torch path
+  python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path, default workload
+  python bench.py --workload {waymo_test,kitti_test,bev_test,waymo_train,fpn_waymo,mc_uncertainty} ...
+  python bench.py --impl reference --gpus N --steps K ...        # the reference's own CPU torch path
 
-Workload = BASELINE.json configs[1], inference stage: synthetic Waymo camera frames
-(1280x1920 -> 80x120 stride-16 grid, A=25, N=240 000 anchors, 6000 -> 300 proposals, res101 C4
-feature map C=1024, 7x7 RoIAlign with sampling_ratio 2).  A "step" is one pass of the hot path
-over one batch of `--frames` independent frames per GPU; frames are sharded one stream per GPU
-with no data-path collective (weak scaling); the only NCCL call is the end-of-stream gather of
-the detection records.  Inputs live in HBM before the timed region (`value`); `e2e` repeats the
-measurement through the host-buffer C-ABI entry (H2D + kernels + D2H inside the timed region).
+Default workload = BASELINE.json configs[1], inference stage: synthetic Waymo camera frames (1280x1920 -> 80x120
+stride-16 grid, A=25, N=240 000 anchors, 6000 -> 300 proposals, res101 C4 feature map C=1024, 7x7 RoIAlign with
+sampling_ratio 2).  The other workloads are the remaining BASELINE.json configs.  A "step" is
+one pass of the hot path over one batch of `--frames` independent frames per GPU; frames are sharded one stream per
+GPU with no data-path collective (weak scaling); the only NCCL call is the end-of-stream gather of the per-frame
+records.  Inputs live in HBM before the timed region (`value`); `e2e` repeats the measurement with HOST buffers
+(H2D + kernels + D2H inside the timed region; the C-ABI `b2d_proposal_crop_host` for the inference workloads).
+
+Beside the measured numbers every line of an inference workload carries
+  * `parity_gate`: after the timed region the outputs of frame 0 and frame F-1 are checked against the oracle
+    (selection order and NMS keep list exact, pooled features to 1e-5 against torchvision-CPU); the run fails
+    otherwise;
+  * `gpu_baseline`: the reference's own functions on the same B200 through torchvision's stock CUDA kernels
+    (`proposal_layer` -> `torchvision.ops.nms`, `torchvision.ops.roi_align`), same inputs, CUDA-event timed;
+  * `latency_ms_f1`: one frame per call, which is what the reference API issues (`assert num_frames == 1`);
+  * `cpu_baseline`: the reference's CPU torch path on a bounded sample (kind "reference" = the unmodified
+    reference functions from /root/reference or its staged copy oracle/_ref, "port" = the oracle restatement).
 """
 import argparse
 import json
@@ -28,41 +39,92 @@ import numpy as np
 import torch
 
 SCALES, RATIOS = [2, 4, 8, 16, 32], [0.5, 0.75, 1, 1.25, 2]
-CFG = dict(name="waymo_image_test_1280x1920_res101_c4", frame_hw=(1280, 1920), Hf=80, Wf=120, A=25, C=1024,
-           pre_nms=6000, post_nms=300, nms_thresh=0.7, pooled=7, sampling_ratio=2, stride=16)
 METRIC = "proposal+NMS+RoI-crop frames/s"
+_INF = dict(pre_nms=6000, post_nms=300, nms_thresh=0.7, pooled=7, sampling_ratio=2, stride=16, C=1024, kind="inference")
+WORKLOADS = {
+    "waymo_test": dict(_INF, name="waymo_image_test_1280x1920_res101_c4", net="image", frame_hw=(1280, 1920),
+                       Hf=80, Wf=120, A=25, frames=128),
+    "kitti_test": dict(_INF, name="kitti_image_test_375x1242_res101_c4", net="image", frame_hw=(375, 1242),
+                       Hf=24, Wf=78, A=25, frames=128),
+    "bev_test": dict(_INF, name="waymo_lidar_bev_test_800x700_res101_c4", net="lidar", frame_hw=(800, 700),
+                     Hf=50, Wf=44, A=2, frames=128),
+    "waymo_train": dict(_INF, name="waymo_image_train_1280x1920_res101_c4", net="image", frame_hw=(1280, 1920), Hf=80,
+                        Wf=120, A=25, frames=8, kind="train", pre_nms=12000, post_nms=2000, rois=256, G=32, K=2),
+    "fpn_waymo": dict(_INF, name="waymo_image_test_fpn_p2_p5", net="image", frame_hw=(1280, 1920), A=25, C=256,
+                      levels=[(320, 480, 4), (160, 240, 8), (80, 120, 16), (40, 60, 32)], frames=4, kind="fpn"),
+    "mc_uncertainty": dict(name="mc_dropout_T20_lidar_head_tail", net="lidar", frame_hw=(800, 700), T=20, R=300, K=2,
+                           E=7, frames=64, kind="mc", score_thresh=0.1, nms_thresh=0.6, max_dets=100),
+}
 
 
-def algorithmic_bytes(cfg, rois_per_frame):
-    """SURVEY.md §8(d): per-frame algorithmic bytes of the fused inference stage (fp32)."""
-    N = cfg["Hf"] * cfg["Wf"] * cfg["A"]
-    b_prop = N * 4 + N * 16
-    b_nms = 2 * cfg["pre_nms"] * 20 + cfg["post_nms"] * 24
-    b_crop = cfg["C"] * cfg["Hf"] * cfg["Wf"] * 4 + rois_per_frame * cfg["C"] * cfg["pooled"] ** 2 * 4
-    return b_prop, b_nms, b_crop
+# ------------------------------------------------------------------------------------------
+# synthetic inputs (generator seeded 3 + frame index, model/config.py:346)
+# ------------------------------------------------------------------------------------------
+def synth_rpn(n_loc_shape, A, g, device):
+    logits = torch.randn(*n_loc_shape, 2 * A, generator=g, device=device)
+    pair = torch.stack((logits[..., :A], logits[..., A:]), -1).softmax(-1)
+    prob = torch.cat((pair[..., 0], pair[..., 1]), -1)
+    d = torch.randn(*n_loc_shape, A, 4, generator=g, device=device)
+    d[..., :2] *= 0.1
+    d[..., 2:] *= 0.2
+    return prob, d.reshape(*n_loc_shape, 4 * A)
 
 
 def synth_frames(cfg, F, device, first_frame):
-    """SURVEY.md §8d inputs, generator seeded 3 + frame index (model/config.py:346)."""
     Hf, Wf, A, C = cfg["Hf"], cfg["Wf"], cfg["A"], cfg["C"]
     prob = torch.empty(F, Hf, Wf, 2 * A, device=device)
     deltas = torch.empty(F, Hf, Wf, 4 * A, device=device)
     feat = torch.empty(F, C, Hf, Wf, device=device)
     for i in range(F):
         g = torch.Generator(device=device).manual_seed(3 + first_frame + i)
-        logits = torch.randn(Hf, Wf, 2 * A, generator=g, device=device)
-        pair = torch.stack((logits[..., :A], logits[..., A:]), -1).softmax(-1)
-        prob[i] = torch.cat((pair[..., 0], pair[..., 1]), -1)
-        d = torch.randn(Hf, Wf, A, 4, generator=g, device=device)
-        d[..., :2] *= 0.1
-        d[..., 2:] *= 0.2
-        deltas[i] = d.reshape(Hf, Wf, 4 * A)
+        prob[i], deltas[i] = synth_rpn((Hf, Wf), A, g, device)
         feat[i] = torch.randn(C, Hf, Wf, generator=g, device=device)
     H, W = cfg["frame_hw"]
-    info = torch.tensor([[0, W, 0, H, 0, 0, 1.0]], device=device).repeat(F, 1)
+    z = 12.0 if cfg["net"] == "lidar" else 0.0                    # minibatch.py:438 / :670
+    info = torch.tensor([[0, W, 0, H, 0, z, 1.0]], device=device).repeat(F, 1)
     return prob, deltas, feat, info
 
 
+def synth_gt(seed, G, W, H, K):
+    """Image GT: w,h log-uniform [16,400] px inside the frame, cls uniform {1..K-1}."""
+    g = torch.Generator().manual_seed(seed)
+    wh = torch.exp(torch.rand(G, 2, generator=g) * (np.log(400.0) - np.log(16.0)) + np.log(16.0))
+    x1 = torch.rand(G, generator=g) * (W - 1 - wh[:, 0])
+    y1 = torch.rand(G, generator=g) * (H - 1 - wh[:, 1])
+    cls = torch.randint(1, max(K, 2), (G,), generator=g).float()
+    return torch.stack((x1, y1, x1 + wh[:, 0], y1 + wh[:, 1], cls), dim=1)
+
+
+def anchors_for(cfg, device):
+    """(anchors [N,4], anchors_3d [N,7] | None) on `device`, product code on CUDA, oracle on CPU."""
+    if device.type == "cuda":
+        from faster_rcnn_pytorch_multimodal_b200.layer_utils.generate_3d_anchors import GridAnchor3dGenerator
+        from faster_rcnn_pytorch_multimodal_b200.layer_utils.snippets import generate_anchors_pre
+        from faster_rcnn_pytorch_multimodal_b200.utils.bbox import bbaa_graphics_gems_torch
+        if cfg["net"] == "lidar":
+            _, a3d = GridAnchor3dGenerator()._generate(cfg["Hf"], cfg["Wf"], cfg["stride"], np.array([1]),
+                                                       np.array([0, np.pi / 2]), 1.0, device=device)
+            return bbaa_graphics_gems_torch(a3d, cfg["Wf"] * cfg["stride"], cfg["Hf"] * cfg["stride"], clip=False), a3d
+        return generate_anchors_pre(cfg["Hf"], cfg["Wf"], cfg["stride"], SCALES, RATIOS, 1.0, device=device)[0], None
+    from oracle import glue_oracle as O
+    if cfg["net"] == "lidar":
+        _, a3d = O.generate_3d_anchors(cfg["Hf"], cfg["Wf"], cfg["stride"], np.array([1]), np.array([0, np.pi / 2]), 1.0)
+        a3d = torch.from_numpy(np.ascontiguousarray(a3d, dtype=np.float32))
+        return O.bbaa_graphics_gems_torch(a3d, cfg["Wf"] * cfg["stride"], cfg["Hf"] * cfg["stride"], clip=False), a3d
+    a = torch.from_numpy(O.generate_anchors_pre(cfg["Hf"], cfg["Wf"], cfg["stride"], SCALES, RATIOS, 1.0)[0])
+    return a, torch.zeros(a.shape[0], 7)
+
+
+def algorithmic_bytes(cfg, rois_per_frame):
+    """SURVEY.md §8(d): per-frame algorithmic bytes of the fused inference stage (fp32)."""
+    N = cfg["Hf"] * cfg["Wf"] * cfg["A"]
+    b_prop = N * 4 + N * 16 + (N * 28 if cfg["net"] == "lidar" else 0)
+    b_nms = 2 * min(cfg["pre_nms"], N) * 20 + cfg["post_nms"] * 24
+    b_crop = cfg["C"] * cfg["Hf"] * cfg["Wf"] * 4 + rois_per_frame * cfg["C"] * cfg["pooled"] ** 2 * 4
+    return b_prop, b_nms, b_crop
+
+
+# ------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -111,42 +173,841 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_reference_frames_per_s(cfg, n_frames, warmup, threads):
-    """The reference's CPU torch path (oracle port): proposal_layer -> torchvision roi_align."""
+def bind_host(local_rank, n_local):
+    """Pin this rank's CPU affinity to its share of the GPU's NUMA node BEFORE any pinned buffer is allocated
+    (first touch then places the staging pages next to the GPU's root complex)."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/"
+        node = int(open(path + "numa_node").read().strip())
+        cpus = sorted(os.sched_getaffinity(0))
+        if node >= 0 and os.path.exists(f"/sys/devices/system/node/node{node}/cpulist"):
+            txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            local = []
+            for part in txt.split(","):
+                a, _, b = part.partition("-")
+                local += list(range(int(a), int(b or a) + 1))
+            cpus = [c for c in cpus if c in local] or cpus
+        share = cpus[local_rank % max(n_local, 1)::max(n_local, 1)] or cpus
+        os.sched_setaffinity(0, share)
+        return {"numa_node": node, "cpus": len(share), "cpus_on_node": len(cpus)}
+    except Exception as e:   # sysfs layout differs on some VMs: the binding is an optimisation, not a requirement
+        return {"numa_node": None, "error": type(e).__name__}
+
+
+class Harness:
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.binding = bind_host(self.local, int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world))))
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        from faster_rcnn_pytorch_multimodal_b200 import _lib
+        self.L = _lib.lib()
+        self.sampler = ClockSampler(self.local)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def gather_records(self, rec):
+        """The path's only collective: end-of-stream gather of the per-frame records (stream.gather_detections)."""
+        if self.dist is not None:
+            self.dist.all_gather([torch.empty_like(rec) for _ in range(self.world)], rec)
+
+    def time_steps(self, step, record_fn=None, sample_clocks=True):
+        """W warm-ups, barrier + sync, exactly K steps between CUDA events, the gather, barrier + sync; max over ranks."""
+        a = self.args
+        if sample_clocks and self.rank == 0:
+            self.sampler.start()
+        out = None
+        for _ in range(a.warmup):
+            out = step()
+        if record_fn is not None:
+            self.gather_records(record_fn(out))      # warm the communicator: the first collective builds its channels
+        self.barrier()
+        wall0 = time.perf_counter()
+        l0 = self.L.b2d_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            out = step()
+        if record_fn is not None:
+            self.gather_records(record_fn(out))
+        e1.record()
+        self.barrier()
+        wall1 = time.perf_counter()
+        launches = self.L.b2d_launch_count() - l0
+        (ms,) = self.max_over_ranks(e0.elapsed_time(e1))
+        clocks = self.sampler.stop(wall0, wall1) if (sample_clocks and self.rank == 0) else None
+        return ms, int(launches), clocks, out
+
+    def time_simple(self, fn, iters, warmup=3):
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))[0] / iters
+
+    def finish(self, line):
+        if self.rank == 0:
+            print(json.dumps(line), flush=True)
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def host_ceiling():
+    p = os.path.join(ROOT, "profiles", "r02_host_ceiling.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own functions (unmodified, from /root/reference or oracle/_ref) or the oracle port
+# ------------------------------------------------------------------------------------------
+def load_reference():
+    from oracle import ref_import
+    if ref_import.available():
+        try:
+            return ref_import.load(), ref_import.source()
+        except Exception as e:       # the port below always exists
+            sys.stderr.write(f"reference import failed ({e!r}); falling back to the oracle port\n")
+    return None, None
+
+
+def cpu_frame_fn(cfg, ref):
+    """Returns (fn(frame_index) -> None running ONE frame of the workload on the CPU, kind string)."""
     from oracle import glue_oracle as O
+    cpu = torch.device("cpu")
+    kind = cfg["kind"]
+    if kind == "inference":
+        anchors, a3 = anchors_for(cfg, cpu)
+        if ref is not None:
+            rc = ref.cfg
+            rc.TEST.RPN_PRE_NMS_TOP_N, rc.TEST.RPN_POST_NMS_TOP_N, rc.TEST.RPN_NMS_THRESH = \
+                cfg["pre_nms"], cfg["post_nms"], cfg["nms_thresh"]
+            import torchvision
+
+            def run(i):
+                prob, deltas, feat, info = synth_frames(cfg, 1, cpu, i)
+                t0 = time.perf_counter()
+                blob, _, _ = ref.pl.proposal_layer(prob, deltas, info[0].numpy(), "TEST", anchors, a3, cfg["A"])
+                torchvision.ops.roi_align(feat, blob, (cfg["pooled"],) * 2, 1.0 / cfg["stride"], cfg["sampling_ratio"])
+                return time.perf_counter() - t0
+            return run, "reference"
+        ocfg = O.GlueCfg(test_pre_nms=cfg["pre_nms"], test_post_nms=cfg["post_nms"], test_nms_thresh=cfg["nms_thresh"])
+
+        def run(i):
+            prob, deltas, feat, info = synth_frames(cfg, 1, cpu, i)
+            t0 = time.perf_counter()
+            blob, _, _ = O.proposal_layer(prob, deltas, info[0].numpy(), "TEST", anchors, a3, cfg["A"], cfg=ocfg,
+                                          stable_sort=False)
+            O.roi_align(feat, blob, (cfg["pooled"],) * 2, 1.0 / cfg["stride"], cfg["sampling_ratio"], False)
+            return time.perf_counter() - t0
+        return run, "port"
+    if kind == "train":
+        import torchvision
+        anchors, a3 = anchors_for(cfg, cpu)
+        H, W = cfg["frame_hw"]
+        ocfg = O.GlueCfg(net_type="image")
+
+        def run(i):
+            prob, deltas, feat, info = synth_frames(cfg, 1, cpu, i)
+            gt = synth_gt(100 + i, cfg["G"], W, H, cfg["K"])
+            true_gt = torch.zeros(cfg["G"], 8)
+            dc = torch.zeros(0, 5)
+            feat.requires_grad_(True)
+            t0 = time.perf_counter()
+            blob, sc, a3k = O.proposal_layer(prob, deltas, info[0].numpy(), "TRAIN", anchors, a3, cfg["A"], cfg=ocfg,
+                                             stable_sort=False)
+            O.anchor_target_layer(gt, dc, info[0].numpy(), anchors, cfg["A"], cfg["Hf"], cfg["Wf"], cfg=ocfg)
+            out = O.proposal_target_layer(blob, sc, a3k, gt, true_gt, dc, cfg["K"], 4, cfg=ocfg)
+            pooled = torchvision.ops.roi_align(feat, out[1], (7, 7), 1.0 / 16, 2)
+            pooled.backward(torch.ones_like(pooled))
+            return time.perf_counter() - t0
+        return run, "port"
+    if kind == "fpn":
+        H, W = cfg["frame_hw"]
+        anchors = torch.cat([torch.from_numpy(O.generate_anchors_pre(h, w, s, SCALES, RATIOS, 1.0)[0])
+                             for h, w, s in cfg["levels"]])
+        a3 = torch.zeros(anchors.shape[0], 7)
+        ocfg = O.GlueCfg()
+
+        def run(i):
+            g = torch.Generator().manual_seed(3 + i)
+            n_loc = sum(h * w for h, w, _ in cfg["levels"])
+            prob, deltas = synth_rpn((1, 1, n_loc), cfg["A"], g, cpu)
+            feats = [torch.randn(1, cfg["C"], h, w, generator=g) for h, w, _ in cfg["levels"]]
+            info = np.array([0, W, 0, H, 0, 0, 1.0], dtype=np.float32)
+            t0 = time.perf_counter()
+            blob, _, _ = O.proposal_layer(prob, deltas, info, "TEST", anchors, a3, cfg["A"], cfg=ocfg, stable_sort=False)
+            O.multiscale_roi_align(feats, blob[:, 1:5], (H, W), (7, 7), 2)
+            return time.perf_counter() - t0
+        return run, "port"
+    if kind == "mc":
+        def run(i):
+            bs, cs, rois, a3d, info = synth_mc(cfg, 1, cpu, i)
+            t0 = time.perf_counter()
+            mc_oracle_frame(cfg, bs[:, 0], cs[:, 0], rois[0], a3d[0], info[0])
+            return time.perf_counter() - t0
+        return run, "port"
+    raise KeyError(kind)
+
+
+def cpu_frames_per_s(cfg, n_frames, warmup, threads, ref):
     torch.set_num_threads(threads)
-    anchors = torch.from_numpy(O.generate_anchors_pre(cfg["Hf"], cfg["Wf"], cfg["stride"], SCALES, RATIOS, 1.0)[0])
-    a3 = torch.zeros(anchors.shape[0], 7)
-    ocfg = O.GlueCfg(test_pre_nms=cfg["pre_nms"], test_post_nms=cfg["post_nms"], test_nms_thresh=cfg["nms_thresh"])
+    run, kind = cpu_frame_fn(cfg, ref)
     times = []
     for i in range(warmup + n_frames):
-        prob, deltas, feat, info = synth_frames(cfg, 1, torch.device("cpu"), i)
-        t0 = time.perf_counter()
-        blob, _, _ = O.proposal_layer(prob, deltas, info[0].numpy(), "TEST", anchors, a3, cfg["A"], cfg=ocfg,
-                                      stable_sort=False)
-        O.roi_align(feat, blob, (cfg["pooled"],) * 2, 1.0 / cfg["stride"], cfg["sampling_ratio"], False)
-        dt = time.perf_counter() - t0
+        dt = run(i)
         if i >= warmup:
             times.append(dt)
-    return len(times) / sum(times), float(np.median(times))
+    return len(times) / sum(times), float(np.median(times)), kind
 
 
-def run_reference(args, rank, world):
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     per_step = max(1, args.ref_frames_per_step)
-    fps, med = cpu_reference_frames_per_s(CFG, args.steps * per_step, args.warmup, threads)
-    sample = f"{args.steps * per_step} frames of {CFG['name']} after {args.warmup} warm-up frames, {threads} torch threads"
+    ref, src = load_reference()
+    fps, med, kind = cpu_frames_per_s(cfg, args.steps * per_step, args.warmup, threads, ref)
+    what = ("the UNMODIFIED reference functions (" + src + "): proposal_layer + torchvision.ops.roi_align"
+            if kind == "reference" else "oracle restatement of the reference path (oracle/glue_oracle.py)")
+    sample = f"{args.steps * per_step} frames of {cfg['name']} after {args.warmup} warm-up frames, {threads} torch threads, {what}"
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step / fps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CFG["name"], "frames_per_step": per_step, "pre_nms": CFG["pre_nms"],
-                       "post_nms": CFG["post_nms"], "channels": CFG["C"], "device": "host CPU"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+            "config": workload_config(cfg, per_step, "host CPU"),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample,
                              "median_ms_per_frame": 1e3 * med},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, F, parallelism):
+    c = {"workload": cfg["name"], "frames_per_step_per_gpu": F, "parallelism": parallelism}
+    for k_src, k_dst in (("pre_nms", "pre_nms"), ("post_nms", "post_nms"), ("C", "channels"), ("pooled", "pooled"),
+                         ("sampling_ratio", "sampling_ratio"), ("T", "mc_samples"), ("rois", "sampled_rois")):
+        if k_src in cfg:
+            c[k_dst] = cfg[k_src]
+    return c
+
+
+def add_cpu_baseline(line, args, cfg):
+    if args.no_cpu_baseline:
+        return
+    threads = os.cpu_count() or 1
+    ref, src = load_reference()
+    fps, med, kind = cpu_frames_per_s(cfg, args.cpu_baseline_frames, 1, threads, ref)
+    line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                            "sample": f"{args.cpu_baseline_frames} frames of {cfg['name']} after 1 warm-up, {threads} threads, "
+                                      + ("unmodified reference functions (" + src + ")" if kind == "reference"
+                                         else "oracle restatement of the reference path"),
+                            "median_ms_per_frame": 1e3 * med}
+
+
+# ------------------------------------------------------------------------------------------
+# inference workloads: proposal_layer + RoIAlign forward (waymo_test / kitti_test / bev_test)
+# ------------------------------------------------------------------------------------------
+def torchvision_cuda_baseline(h, cfg, prob, deltas, feat, info, anchors, a3d, iters):
+    """The bar to beat: the reference's proposal_layer on CUDA tensors - scores.sort ->
+    torchvision.ops.nms (proposal_layer.py:32-55) - looped per frame as the reference does, then ONE batched
+    torchvision.ops.roi_align (torchpoolers.py:165-170) over all frames; plus the same at one frame per call."""
+    try:
+        import torchvision
+    except Exception as e:
+        return {"unavailable": f"torchvision import failed: {type(e).__name__}"}
+    from oracle import glue_oracle as O
+    ref, src = load_reference()
+    F = prob.shape[0]
+    a3 = a3d if a3d is not None else torch.zeros(anchors.shape[0], 7, device=anchors.device)
+    info_np = info[0].cpu().numpy()
+    if ref is not None:
+        rc = ref.cfg
+        rc.TEST.RPN_PRE_NMS_TOP_N, rc.TEST.RPN_POST_NMS_TOP_N, rc.TEST.RPN_NMS_THRESH = \
+            cfg["pre_nms"], cfg["post_nms"], cfg["nms_thresh"]
+        prop = lambda f: ref.pl.proposal_layer(prob[f:f + 1], deltas[f:f + 1], info_np, "TEST", anchors, a3, cfg["A"])[0]
+        what = "unmodified reference proposal_layer (" + src + ") on CUDA tensors"
+    else:
+        ocfg = O.GlueCfg(test_pre_nms=cfg["pre_nms"], test_post_nms=cfg["post_nms"], test_nms_thresh=cfg["nms_thresh"])
+        prop = lambda f: O.proposal_layer(prob[f:f + 1], deltas[f:f + 1], info_np, "TEST", anchors, a3, cfg["A"],
+                                          cfg=ocfg, stable_sort=False)[0]
+        what = "oracle port of proposal_layer on CUDA tensors"
+    P, sc, sr = cfg["pooled"], 1.0 / cfg["stride"], cfg["sampling_ratio"]
+
+    def batch():
+        blobs = []
+        for f in range(F):
+            b = prop(f)
+            b[:, 0] = f
+            blobs.append(b)
+        return torchvision.ops.roi_align(feat, torch.cat(blobs), (P, P), sc, sr)
+
+    def single():
+        return torchvision.ops.roi_align(feat[:1], prop(0), (P, P), sc, sr)
+
+    def events(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    ms_batch = events(batch, max(2, iters))
+    ms_f1 = events(single, 10)
+    blobs = torch.cat([prop(f) for f in range(F)])
+    ms_nms_sort = events(lambda: [prop(f) for f in range(F)], 2)
+    ms_roi = events(lambda: torchvision.ops.roi_align(feat, blobs, (P, P), sc, sr), 3)
+    return {"value": F / (ms_batch * 1e-3), "unit": "frames/s", "ms_per_frame": ms_batch / F, "f1_ms": ms_f1,
+            "proposal_layer_ms_per_frame": ms_nms_sort / F, "roi_align_ms_per_frame": ms_roi / F,
+            "frames_per_step": F, "what": what + " + torchvision.ops.roi_align (stock sm_100 kernels), median of CUDA-event timings"}
+
+
+def parity_gate_inference(cfg, ops, dev, prob, deltas, feat, info, anchors, a3d, rois, scores, num, pooled):
+    """Frames 0 and F-1 of the timed batch against the oracle: selection order and keep list exact (NMS re-run on
+    OUR decoded boxes by torchvision-CPU), decoded boxes 1e-3 abs, pooled features 1e-5 vs torchvision-CPU."""
+    from oracle import glue_oracle as O
+    F, A = prob.shape[0], cfg["A"]
+    n_loc = cfg["Hf"] * cfg["Wf"]
+    M = cfg["post_nms"]
+    sb, ss, si = ops.proposal_sorted_debug(F, n_loc, A, cfg["pre_nms"], M, dev)
+    anc_cpu = anchors.cpu()
+    checked = []
+    for f in sorted({0, F - 1}):
+        sc_all = prob[f, :, :, A:].contiguous().view(-1).cpu()
+        o_sc, o_ord = sc_all.sort(descending=True, stable=True)
+        k = sb.shape[1]
+        if not torch.equal(si[f].cpu().long(), o_ord[:k]) or not torch.equal(ss[f].cpu(), o_sc[:k]):
+            return f"frame {f}: pre-NMS selection order differs from the stable oracle sort"
+        o_boxes = O.clip_boxes(O.bbox_transform_inv(anc_cpu, deltas[f].reshape(-1, 4).cpu()), info[f].cpu().numpy())[o_ord[:k]]
+        if not torch.allclose(sb[f].cpu(), o_boxes, rtol=1e-5, atol=1e-3):
+            return f"frame {f}: decoded boxes differ"
+        keep = O.nms(sb[f].cpu(), ss[f].cpu(), cfg["nms_thresh"])[:M]
+        n = int(num[f])
+        if n != keep.numel() or not torch.equal(rois[f, :n, 1:].cpu(), sb[f].cpu()[keep]):
+            return f"frame {f}: NMS keep list differs from torchvision-CPU on the same boxes"
+        if not torch.equal(scores[f, :n].cpu(), ss[f].cpu()[keep]):
+            return f"frame {f}: kept scores differ"
+        blob = rois[f, :n].cpu().clone()
+        blob[:, 0] = 0
+        want = O.roi_align(feat[f:f + 1].cpu(), blob, (cfg["pooled"],) * 2, 1.0 / cfg["stride"], cfg["sampling_ratio"], False)
+        got = pooled.view(F, M, cfg["C"], cfg["pooled"], cfg["pooled"])[f, :n].cpu()
+        if not torch.allclose(got, want, rtol=1e-5, atol=1e-5):
+            return f"frame {f}: pooled features differ from torchvision-CPU by {float((got - want).abs().max()):.3g}"
+        if n < M and float(pooled.view(F, M, -1)[f, n:].abs().max()) != 0.0:
+            return f"frame {f}: padded RoI rows are not zero"
+        checked.append(f)
+    return "ok"
+
+
+def run_inference(args, cfg):
+    h = Harness(args)
+    dev, rank, world = h.dev, h.rank, h.world
+    from faster_rcnn_pytorch_multimodal_b200 import _lib, ops
+    L = h.L
+    F = args.frames or cfg["frames"]
+    A, P, M = cfg["A"], cfg["pooled"], cfg["post_nms"]
+    n_loc = cfg["Hf"] * cfg["Wf"]
+    anchors, a3d = anchors_for(cfg, dev)
+    prob, deltas, feat, info = synth_frames(cfg, F, dev, first_frame=rank * F)
+    pooled = torch.empty(F * M, cfg["C"], P, P, device=dev)
+    crop_events = []
+
+    def step():
+        rois, scores, a3k, _, num = ops.proposal_batched(prob, deltas, info, anchors, a3d, A, cfg["pre_nms"], M,
+                                                         cfg["nms_thresh"], batch_index_stride=1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops._roi_align_forward(feat, rois.view(-1, 5), (P, P), 1.0 / cfg["stride"], cfg["sampling_ratio"], False,
+                               seg_count=num, seg_stride=M, out=pooled)
+        e1.record()
+        crop_events.append((e0, e1))
+        return rois, scores, num
+
+    record = lambda o: torch.cat((o[0].view(F, -1), o[1], o[2].view(F, 1).float()), dim=1)
+    elapsed_ms, launches, clocks, (rois, scores, num) = h.time_steps(step, record)
+    crop_ms = float(np.mean([a.elapsed_time(b) for a, b in crop_events[-args.steps:]]))
+    (crop_ms,) = h.max_over_ranks(crop_ms)
+    n_rois = int(num.sum().item())
+    value = world * F * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- single-frame latency (what the reference API issues: one frame per call)
+    p1, d1, f1, i1 = prob[:1], deltas[:1], feat[:1], info[:1]
+    pool1 = torch.empty(M, cfg["C"], P, P, device=dev)
+
+    def one_frame():
+        r, _, _, _, n = ops.proposal_batched(p1, d1, i1, anchors, a3d, A, cfg["pre_nms"], M, cfg["nms_thresh"])
+        ops._roi_align_forward(f1, r.view(-1, 5), (P, P), 1.0 / cfg["stride"], cfg["sampling_ratio"], False,
+                               seg_count=n, seg_stride=M, out=pool1)
+    lat_ms = h.time_simple(one_frame, 50)
+    lat_prop_ms = h.time_simple(lambda: ops.proposal_batched(p1, d1, i1, anchors, a3d, A, cfg["pre_nms"], M,
+                                                             cfg["nms_thresh"]), 50)
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
+    Fe = max(1, min(args.e2e_frames, F))
+    pin = lambda t: t.cpu().pin_memory()
+    hp, hd, hf, hi = pin(prob[:Fe]), pin(deltas[:Fe]), pin(feat[:Fe]), pin(info[:Fe])
+    o_rois = torch.empty(Fe, M, 5).pin_memory()
+    o_sc = torch.empty(Fe, M).pin_memory()
+    o_num = torch.empty(Fe, dtype=torch.int32).pin_memory()
+    o_pool = torch.empty(Fe * M, cfg["C"], P, P).pin_memory()
+    ws = torch.empty(L.b2d_pipeline_device_bytes(Fe, n_loc, A, cfg["C"], cfg["Hf"], cfg["Wf"], cfg["pre_nms"], M, P),
+                     dtype=torch.uint8, device=dev)
+
+    def e2e_step():
+        _lib.check(L.b2d_proposal_crop_host(Fe, n_loc, A, cfg["C"], cfg["Hf"], cfg["Wf"], _lib.ptr(hp), _lib.ptr(hd),
+                                            _lib.ptr(hi), _lib.ptr(anchors), _lib.ptr(hf), cfg["pre_nms"], M,
+                                            cfg["nms_thresh"], P, 1.0 / cfg["stride"], cfg["sampling_ratio"],
+                                            _lib.ptr(o_rois), _lib.ptr(o_sc), _lib.ptr(o_num), _lib.ptr(o_pool),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "b2d_proposal_crop_host")
+    e_steps = max(3, args.steps // 2)
+    e2e_ms = h.time_simple(e2e_step, e_steps) * e_steps
+    e2e_value = world * Fe * e_steps / (e2e_ms * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (hp, hd, hf, hi))
+    d2h = sum(t.numel() * t.element_size() for t in (o_rois, o_sc, o_num, o_pool))
+
+    # ---- parity gate (after the timed regions; the run fails if it does not hold)
+    gate = parity_gate_inference(cfg, ops, dev, prob, deltas, feat, info, anchors, a3d, rois, scores, num, pooled)
+    if gate == "ok":
+        ok_host = torch.equal(o_num, num[:Fe].cpu()) and torch.equal(o_rois, rois[:Fe].cpu()) and \
+            torch.equal(o_pool.view(Fe, -1)[Fe - 1], pooled.view(F, -1)[Fe - 1].cpu())
+        if not ok_host:
+            gate = "host-buffer entry disagrees with the device path"
+    (gate_bad,) = h.max_over_ranks(0.0 if gate == "ok" else 1.0)
+    if gate != "ok":
+        sys.stderr.write(f"[rank {rank}] PARITY GATE FAILED: {gate}\n")
+    if gate_bad:
+        raise SystemExit(3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        b_prop, b_nms, b_crop = algorithmic_bytes(cfg, n_rois / F)
+        crop_gbs = F * b_crop / (crop_ms * 1e-3) / 1e9
+        step_gbs = F * (b_prop + b_nms + b_crop) / (elapsed_ms / args.steps * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
+        if os.path.exists(tp) and cfg["name"].startswith("waymo_image_test"):
+            tj = json.load(open(tp))            # one ncu --set full capture, scaled to this run's frames per launch
+            traffic = tj["dram_bytes_per_launch"] * F / tj["frames_in_launch"]
+        conf = workload_config(cfg, F, f"frame-stream x{world}, no data-path collective")
+        conf.update(anchors_per_frame=n_loc * A, rois_per_frame=n_rois / F,
+                    l2_policy=f"inputs larger than L2 ({F * (b_prop + cfg['C'] * n_loc * 4) / 1e6:.0f} MB read, "
+                              f"{F * M * cfg['C'] * P * P * 4 / 1e6:.0f} MB written per step)")
+        ceil = host_ceiling()
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "frames_per_call": Fe, "ms_per_call": e2e_ms / e_steps, "host_binding": h.binding,
+               "note": "PCIe-bound: H2D of scores/deltas/features and D2H of the pooled features per frame; frames "
+                       "pipelined over H2D / compute / D2H streams"}
+        gbs = world * (h2d + d2h) * e_steps / (e2e_ms * 1e-3) / 1e9
+        e2e["host_link_gbs"] = gbs
+        if ceil and str(world) in ceil.get("aggregate_duplex_gbs", {}):
+            e2e["ceiling_gbs"] = ceil["aggregate_duplex_gbs"][str(world)]
+            e2e["frac_of_ceiling"] = gbs / e2e["ceiling_gbs"]
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
+            "roofline": {"bound": "hbm", "kernel": "rows::fwd_kernel<2,true> (RoIAlign forward)", "achieved": crop_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": crop_gbs / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": F * b_crop, "kernel_ms": crop_ms,
+                         "kernel_share_of_step": crop_ms / (elapsed_ms / args.steps),
+                         "fused_stage": {"achieved": step_gbs, "frac": step_gbs / peak,
+                                         "algorithmic_bytes_per_frame": b_prop + b_nms + b_crop}},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity_gate": gate,
+            "latency_ms_f1": lat_ms, "latency_ms_f1_proposal_layer": lat_prop_ms,
+        }
+        if not args.no_gpu_baseline:
+            Fb = min(F, args.gpu_baseline_frames)
+            line["gpu_baseline"] = torchvision_cuda_baseline(h, cfg, prob[:Fb], deltas[:Fb], feat[:Fb], info[:Fb], anchors,
+                                                             a3d, 3)
+            gb = line["gpu_baseline"]
+            if "value" in gb:
+                gb["speedup_device_resident"] = value / world / gb["value"]
+                gb["speedup_f1"] = gb["f1_ms"] / lat_ms
+        add_cpu_baseline(line, args, cfg)
+    h.finish(line)
+
+
+# ------------------------------------------------------------------------------------------
+# waymo_train: proposal 12000 -> 2000, anchor targets, proposal targets, RoIAlign forward + backward
+# ------------------------------------------------------------------------------------------
+def run_train(args, cfg):
+    h = Harness(args)
+    dev, rank, world = h.dev, h.rank, h.world
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.anchor_target_layer import anchor_target_layer_torch
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.proposal_target_layer import proposal_target_layer
+    from faster_rcnn_pytorch_multimodal_b200.model.config import cfg as pcfg
+    pcfg.NET_TYPE = "image"
+    F = args.frames or cfg["frames"]
+    A, P, R, K = cfg["A"], cfg["pooled"], cfg["rois"], cfg["K"]
+    H, W = cfg["frame_hw"]
+    anchors, _ = anchors_for(cfg, dev)
+    a3d = torch.zeros(anchors.shape[0], 7, device=dev)
+    prob, deltas, feat, info = synth_frames(cfg, F, dev, first_frame=rank * F)
+    gts = [synth_gt(100 + rank * F + f, cfg["G"], W, H, K).to(dev) for f in range(F)]
+    true_gt = torch.zeros(cfg["G"], 8, device=dev)
+    dc = torch.zeros(0, 5, device=dev)
+    grad_out = torch.randn(F * R, cfg["C"], P, P, device=dev)
+    info_np = info[0].cpu().numpy()
+    stage_ms = {"proposal": [], "targets": [], "roi_fwd_bwd": []}
+
+    def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        rois, scores, a3k, _, num = ops.proposal_batched(prob, deltas, info, anchors, a3d, A, cfg["pre_nms"],
+                                                         cfg["post_nms"], cfg["nms_thresh"], batch_index_stride=0)
+        ev[1].record()
+        nn = num.tolist()                                    # the reference's own host sync (keep.numel())
+        sampled = []
+        for f in range(F):
+            anchor_target_layer_torch(gts[f], dc, info_np, anchors, A, cfg["Hf"], cfg["Wf"], dev)
+            out = proposal_target_layer(rois[f, :nn[f]], scores[f, :nn[f]].view(-1, 1), a3k[f, :nn[f]], gts[f], true_gt,
+                                        dc, K, 4)
+            r = out[1].clone()
+            r[:, 0] = f
+            sampled.append(r)
+        sampled = torch.cat(sampled)
+        ev[2].record()
+        pooled = ops._roi_align_forward(feat, sampled, (P, P), 1.0 / cfg["stride"], cfg["sampling_ratio"], False)
+        gfeat = ops._roi_align_backward(grad_out[:sampled.shape[0]], sampled, tuple(feat.shape), (P, P), 1.0 / cfg["stride"],
+                                        cfg["sampling_ratio"], False)
+        ev[3].record()
+        stage_ms["_ev"] = ev
+        return pooled, gfeat, sampled
+
+    def step_timed():
+        out = step()
+        torch.cuda.synchronize()
+        ev = stage_ms.pop("_ev")
+        for k, (a, b) in zip(("proposal", "targets", "roi_fwd_bwd"), zip(ev[:-1], ev[1:])):
+            stage_ms[k].append(a.elapsed_time(b))
+        return out
+
+    record = lambda o: o[2].reshape(1, -1)[:, :F * R * 5].contiguous()
+    elapsed_ms, launches, clocks, (pooled, gfeat, sampled) = h.time_steps(step, record)
+    for _ in range(3):
+        step_timed()
+    value = world * F * args.steps / (elapsed_ms * 1e-3)
+
+    # e2e through the public API with host inputs: pinned RPN maps + features up, pooled features + grad_feat down
+    pin = lambda t: t.cpu().pin_memory()
+    hp, hd, hf = pin(prob[:1]), pin(deltas[:1]), pin(feat[:1])
+    o_pool, o_g = torch.empty(R, cfg["C"], P, P).pin_memory(), torch.empty(1, cfg["C"], cfg["Hf"], cfg["Wf"]).pin_memory()
+
+    def e2e_step():
+        p, d, ft = hp.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hf.to(dev, non_blocking=True)
+        rois, scores, a3k, _, num = ops.proposal_batched(p, d, info[:1], anchors, a3d, A, cfg["pre_nms"], cfg["post_nms"],
+                                                         cfg["nms_thresh"], batch_index_stride=0)
+        n = int(num[0])
+        anchor_target_layer_torch(gts[0], dc, info_np, anchors, A, cfg["Hf"], cfg["Wf"], dev)
+        out = proposal_target_layer(rois[0, :n], scores[0, :n].view(-1, 1), a3k[0, :n], gts[0], true_gt, dc, K, 4)
+        pl = ops._roi_align_forward(ft, out[1], (P, P), 1.0 / cfg["stride"], cfg["sampling_ratio"], False)
+        gf = ops._roi_align_backward(grad_out[:R], out[1], tuple(ft.shape), (P, P), 1.0 / cfg["stride"],
+                                     cfg["sampling_ratio"], False)
+        o_pool.copy_(pl, non_blocking=True)
+        o_g.copy_(gf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e_ms = h.time_simple(e2e_step, max(3, args.steps // 2))
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        N = cfg["Hf"] * cfg["Wf"] * A
+        fm = cfg["C"] * cfg["Hf"] * cfg["Wf"] * 4
+        b_prop = N * 20 + 2 * cfg["pre_nms"] * 20 + cfg["post_nms"] * 24
+        b_tgt = N * 52 + cfg["G"] * 20 + cfg["post_nms"] * 52 + R * (56 + 3 * K * 4 * 4)
+        b_roi = 2 * (fm + R * cfg["C"] * P * P * 4)
+        roi_ms = float(np.median(stage_ms["roi_fwd_bwd"]))
+        line = {"metric": "proposal+targets+RoI-crop fwd/bwd train frames/s", "value": value, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(cfg, F, f"frame-stream x{world}, no data-path collective"),
+                "roofline": {"bound": "hbm", "kernel": "RoIAlign forward + backward (rows::fwd_kernel, bwd_rows::bwd_kernel)",
+                             "achieved": F * b_roi / (roi_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": F * b_roi / (roi_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": roi_ms, "algorithmic_bytes_per_launch": F * b_roi,
+                             "fused_stage": {"achieved": F * (b_prop + b_tgt + b_roi) / (elapsed_ms / args.steps * 1e-3) / 1e9,
+                                             "algorithmic_bytes_per_frame": b_prop + b_tgt + b_roi}},
+                "stage_ms_per_step": {k: float(np.median(v)) for k, v in stage_ms.items()},
+                "e2e": {"value": world / (e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(hp.nbytes + hd.nbytes + hf.nbytes),
+                        "d2h_bytes_per_step": int(o_pool.nbytes + o_g.nbytes), "frames_per_call": 1,
+                        "note": "public Python API, one frame per call, pinned host tensors in and out"},
+                "gpu_launches": launches, "clocks": clocks,
+                "note": "anchor / proposal targets run one frame per call with the reference's own host syncs "
+                        "(randperm sizes): the target stage is launch- and sync-bound, not bandwidth-bound"}
+        add_cpu_baseline(line, args, cfg)
+    h.finish(line)
+
+
+# ------------------------------------------------------------------------------------------
+# fpn_waymo: RPN over the concatenated pyramid + level-assigned RoI crop (MultiScaleRoIAlign)
+# ------------------------------------------------------------------------------------------
+def run_fpn(args, cfg):
+    from collections import OrderedDict
+    h = Harness(args)
+    dev, rank, world = h.dev, h.rank, h.world
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.snippets import generate_anchors_pre
+    from faster_rcnn_pytorch_multimodal_b200.utils.torchpoolers import MultiScaleRoIAlign
+    F = args.frames or cfg["frames"]
+    A, P, M, C = cfg["A"], cfg["pooled"], cfg["post_nms"], cfg["C"]
+    H, W = cfg["frame_hw"]
+    levels = cfg["levels"]
+    anchors = torch.cat([generate_anchors_pre(hh, ww, s, SCALES, RATIOS, 1.0, device=dev)[0] for hh, ww, s in levels])
+    n_loc = sum(hh * ww for hh, ww, _ in levels)
+    prob = torch.empty(F, 1, n_loc, 2 * A, device=dev)
+    deltas = torch.empty(F, 1, n_loc, 4 * A, device=dev)
+    feats = [torch.empty(F, C, hh, ww, device=dev) for hh, ww, _ in levels]
+    for i in range(F):
+        g = torch.Generator(device=dev).manual_seed(3 + rank * F + i)
+        prob[i], deltas[i] = synth_rpn((1, n_loc), A, g, dev)
+        for ft in feats:
+            ft[i] = torch.randn(ft.shape[1:], generator=g, device=dev)
+    info = torch.tensor([[0, W, 0, H, 0, 0, 1.0]], device=dev).repeat(F, 1)
+    names = [f"p{i + 2}" for i in range(len(levels))]
+    msra = MultiScaleRoIAlign(names, P, cfg["sampling_ratio"])
+    x = OrderedDict(zip(names, feats))
+    stage_ms = {"proposal": [], "crop": []}
+
+    def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        rois, scores, _, _, num = ops.proposal_batched(prob, deltas, info, anchors, None, A, cfg["pre_nms"], M,
+                                                       cfg["nms_thresh"], batch_index_stride=1)
+        ev[1].record()
+        nn = num.tolist()
+        with torch.no_grad():
+            pooled = msra(x, [rois[f, :nn[f], 1:5] for f in range(F)], [(H, W)] * F)
+        ev[2].record()
+        stage_ms["_ev"] = ev
+        return rois, scores, num, pooled
+
+    record = lambda o: torch.cat((o[0].view(F, -1), o[1], o[2].view(F, 1).float()), dim=1)
+    elapsed_ms, launches, clocks, (rois, scores, num, pooled) = h.time_steps(step, record)
+    for _ in range(3):
+        step()
+        torch.cuda.synchronize()
+        ev = stage_ms.pop("_ev")
+        stage_ms["proposal"].append(ev[0].elapsed_time(ev[1]))
+        stage_ms["crop"].append(ev[1].elapsed_time(ev[2]))
+    value = world * F * args.steps / (elapsed_ms * 1e-3)
+    # touched tiles: bytes of the feature rows x columns each RoI reads on its level (upper bound: bounding window)
+    with torch.no_grad():
+        lv = ops.fpn_level_map(rois.view(-1, 5)[:, 1:5].contiguous(), 2, 5)
+        r = rois.view(-1, 5)
+        touched = 0.0
+        for li, (hh, ww, s) in enumerate(levels):
+            sel = r[lv == li]
+            if sel.numel():
+                w_px = ((sel[:, 3] - sel[:, 1]) / s + 2).clamp(max=ww)
+                h_px = ((sel[:, 4] - sel[:, 2]) / s + 2).clamp(max=hh)
+                touched += float((w_px * h_px).sum()) * C * 4
+        touched /= F
+
+    pin = lambda t: t.cpu().pin_memory()
+    hp, hd = pin(prob[:1]), pin(deltas[:1])
+    hfe = [pin(ft[:1]) for ft in feats]
+    o_pool = torch.empty(M, C, P, P).pin_memory()
+
+    def e2e_step():
+        p, d = hp.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
+        xs = OrderedDict((n, t.to(dev, non_blocking=True)) for n, t in zip(names, hfe))
+        ro, _, _, _, n = ops.proposal_batched(p, d, info[:1], anchors, None, A, cfg["pre_nms"], M, cfg["nms_thresh"])
+        k = int(n[0])
+        with torch.no_grad():
+            pl = msra(xs, [ro[0, :k, 1:5]], [(H, W)])
+        o_pool[:k].copy_(pl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e_ms = h.time_simple(e2e_step, max(3, args.steps // 2))
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        N = n_loc * A
+        b_prop = N * 20 + 2 * cfg["pre_nms"] * 20 + M * 24
+        pyramid = sum(C * hh * ww * 4 for hh, ww, _ in levels)
+        out_b = M * C * P * P * 4
+        crop_ms = float(np.median(stage_ms["crop"]))
+        step_s = elapsed_ms / args.steps * 1e-3
+        line = {"metric": "FPN proposal+NMS+level-assigned RoI-crop frames/s", "value": value, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(cfg, F, f"frame-stream x{world}, no data-path collective"), anchors_per_frame=N,
+                               levels=[f"{hh}x{ww}@{s}" for hh, ww, s in levels]),
+                "roofline": {"bound": "hbm", "kernel": "score_hist / score_compact (RPN scores of 5.1 M anchors) + level RoIAlign",
+                             "achieved": F * (b_prop + touched + out_b) / step_s / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": F * (b_prop + touched + out_b) / step_s / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src,
+                             "algorithmic_bytes_per_frame": {"touched_tiles": b_prop + touched + out_b,
+                                                             "whole_pyramid": b_prop + pyramid + out_b},
+                             "frac_whole_pyramid": F * (b_prop + pyramid + out_b) / step_s / 1e9 / peak,
+                             "crop_ms": crop_ms},
+                "stage_ms_per_step": {k: float(np.median(v)) for k, v in stage_ms.items()},
+                "e2e": {"value": world / (e_ms * 1e-3), "unit": "frames/s",
+                        "h2d_bytes_per_step": int(hp.nbytes + hd.nbytes + sum(t.nbytes for t in hfe)),
+                        "d2h_bytes_per_step": int(o_pool.nbytes), "frames_per_call": 1,
+                        "note": "public Python API, one frame per call, pinned host tensors in and out"},
+                "gpu_launches": launches, "clocks": clocks}
+        add_cpu_baseline(line, args, cfg)
+    h.finish(line)
+
+
+# ------------------------------------------------------------------------------------------
+# mc_uncertainty: T = 20 MC-dropout head passes -> mean decode + variance + entropy / MI -> per-class filter
+# ------------------------------------------------------------------------------------------
+def synth_mc(cfg, F, device, first_frame):
+    """bbox_pred samples [T,F,R,K*E] (normalised deltas), cls scores [T,F,R,K], rois [F,R,5], anchors_3d [F,R,7]."""
+    T, R, K, E = cfg["T"], cfg["R"], cfg["K"], cfg["E"]
+    H, W = cfg["frame_hw"]
+    bs = torch.empty(T, F, R, K * E, device=device)
+    cs = torch.empty(T, F, R, K, device=device)
+    rois = torch.zeros(F, R, 5, device=device)
+    a3d = torch.empty(F, R, 7, device=device)
+    for i in range(F):
+        g = torch.Generator(device=device).manual_seed(3 + first_frame + i)
+        mu = torch.randn(R, K * E, generator=g, device=device)
+        bs[:, i] = mu + 0.05 * torch.randn(T, R, K * E, generator=g, device=device)
+        cs[:, i] = torch.randn(R, K, generator=g, device=device) * 2 + 0.3 * torch.randn(T, R, K, generator=g, device=device)
+        wh = torch.rand(R, 2, generator=g, device=device) * 60 + 20
+        xy = torch.rand(R, 2, generator=g, device=device) * torch.tensor([W - 90.0, H - 90.0], device=device)
+        rois[i, :, 1:3], rois[i, :, 3:5] = xy, xy + wh
+        a3d[i] = torch.tensor([0, 0, 0.885, 47.3, 20.8, 1.77, 0.0], device=device)
+    info = torch.tensor([[0, W, 0, H, 0, 12.0, 1.0]], device=device).repeat(F, 1)
+    return bs, cs, rois, a3d, info
+
+
+def mc_oracle_frame(cfg, bs, cs, rois, a3d, info):
+    """One frame of the MC tail on the CPU with the oracle restatements (loss_utils.py:114-141,
+    bbox_transform.py:132-233, config.py:219-223, filter_predictions.py:75-130, test.py:213-221)."""
+    from oracle import glue_oracle as O
+    K, E = cfg["K"], cfg["E"]
+    stds = torch.tensor(O.DEFAULT_CFG.lidar_stds).repeat(K)
+    means = torch.tensor(O.DEFAULT_CFG.lidar_means).repeat(K)
+    mean_pred = bs.mean(0) * stds + means
+    e_var = O.compute_bbox_var(bs * stds + means)
+    boxes = O.lidar_3d_bbox_transform_inv(rois[:, 1:5], a3d.clone(), mean_pred)
+    e_var_dec = O.lidar_3d_uncertainty_transform_inv(rois[:, 1:5], a3d.clone(), mean_pred, e_var)
+    probs = torch.softmax(cs, dim=2).mean(0)
+    ent = O.categorical_entropy(probs)
+    mi = O.categorical_mutual_information(cs)
+    dets = O.filter_detections(probs, boxes, info.numpy(), K, E, "lidar", cfg["score_thresh"], cfg["nms_thresh"],
+                               cfg["max_dets"], uc_row=torch.stack((ent, mi), 1),
+                               uc_cls=e_var_dec.view(-1, 1, K * E))
+    order = O.sort_by_uncertainty(e_var_dec.numpy(), descending=True)
+    return boxes, e_var_dec, probs, ent, mi, dets, order
+
+
+def run_mc(args, cfg):
+    h = Harness(args)
+    dev, rank, world = h.dev, h.rank, h.world
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    F = args.frames or cfg["frames"]
+    T, R, K, E = cfg["T"], cfg["R"], cfg["K"], cfg["E"]
+    bs, cs, rois, a3d, info = synth_mc(cfg, F, dev, rank * F)
+
+    def step():
+        out = ops.head_tail_decode(bs, cs, rois, a3d, info, "lidar")
+        dets, det_roi, counts, o_ur, o_uc = ops.final_detections(
+            out["probs"], out["boxes"], info, E, "lidar", cfg["score_thresh"], cfg["nms_thresh"], cfg["max_dets"],
+            uc_row=torch.stack((out["e_entropy"], out["e_mutual_info"]), 2), uc_cls=out["e_bbox_var"].view(F, R, 1, K * E),
+            max_out=cfg["max_dets"])
+        return out, dets, counts, o_ur, o_uc
+
+    record = lambda o: torch.cat((o[1].reshape(F, -1), o[2].float().reshape(F, -1)), 1)
+    elapsed_ms, launches, clocks, (out, dets, counts, o_ur, o_uc) = h.time_steps(step, record)
+    value = world * F * args.steps / (elapsed_ms * 1e-3)
+    # parity gate: frames 0 and F-1 against the oracle chain
+    gate = "ok"
+    for f in sorted({0, F - 1}):
+        boxes, evd, probs, ent, mi, odets, _ = mc_oracle_frame(cfg, bs[:, f].cpu(), cs[:, f].cpu(), rois[f].cpu(),
+                                                               a3d[f].cpu(), info[f].cpu())
+        chk = [("boxes", out["boxes"][f].cpu(), boxes, 1e-4), ("e_bbox_var", out["e_bbox_var"][f].cpu(), evd, 1e-4),
+               ("probs", out["probs"][f].cpu(), probs, 1e-5), ("e_entropy", out["e_entropy"][f].cpu(), ent, 1e-5),
+               ("e_mutual_info", out["e_mutual_info"][f].cpu(), mi, 1e-5)]
+        for name, got, want, tol in chk:
+            if not torch.allclose(got, want, rtol=tol, atol=tol):
+                gate = f"frame {f}: {name} differs by {float((got - want).abs().max()):.3g}"
+        for j in range(1, K):
+            n = int(counts[f, j])
+            if n != len(odets[j]["dets"]) or not np.allclose(dets[f, j, :n].cpu().numpy(), odets[j]["dets"], rtol=1e-4, atol=1e-4):
+                gate = f"frame {f}: final detections of class {j} differ"
+    (bad,) = h.max_over_ranks(0.0 if gate == "ok" else 1.0)
+    if gate != "ok":
+        sys.stderr.write(f"[rank {rank}] PARITY GATE FAILED: {gate}\n")
+    if bad:
+        raise SystemExit(3)
+    pin = lambda t: t.cpu().pin_memory()
+    hb, hc = pin(bs[:, :1]), pin(cs[:, :1])
+    o_d = torch.empty(1, K, cfg["max_dets"], E + 1).pin_memory()
+
+    def e2e_step():
+        b, c = hb.to(dev, non_blocking=True), hc.to(dev, non_blocking=True)
+        o = ops.head_tail_decode(b, c, rois[:1], a3d[:1], info[:1], "lidar")
+        d, _, _, _, _ = ops.final_detections(o["probs"], o["boxes"], info[:1], E, "lidar", cfg["score_thresh"],
+                                             cfg["nms_thresh"], cfg["max_dets"], max_out=cfg["max_dets"])
+        o_d.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e_ms = h.time_simple(e2e_step, max(3, args.steps // 2))
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        b_in = T * R * (K * E + K) * 4 + R * (5 + 7) * 4
+        b_out = R * (2 * K * E + K + 2) * 4 + K * cfg["max_dets"] * (E + 1 + 2 + K * E) * 4
+        step_s = elapsed_ms / args.steps * 1e-3
+        line = {"metric": "MC-dropout head-tail (T=20 decode + variance + entropy/MI + per-class filter) frames/s",
+                "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": workload_config(cfg, F, f"frame-stream x{world}, no data-path collective"),
+                "roofline": {"bound": "hbm", "kernel": "head_tail_kernel + final_detections_kernel",
+                             "achieved": F * (b_in + b_out) / step_s / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": F * (b_in + b_out) / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_frame": b_in + b_out,
+                             "note": "0.4 MB per frame: launch-latency bound, the figure is reported for completeness"},
+                "e2e": {"value": world / (e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(hb.nbytes + hc.nbytes),
+                        "d2h_bytes_per_step": int(o_d.nbytes), "frames_per_call": 1},
+                "gpu_launches": launches, "clocks": clocks, "parity_gate": gate}
+        add_cpu_baseline(line, args, cfg)
+    h.finish(line)
 
 
 def main():
@@ -155,180 +1016,24 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=128, help="independent frames per step per GPU")
+    ap.add_argument("--workload", default="waymo_test", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="independent frames per step per GPU (0: the workload's default)")
     ap.add_argument("--e2e-frames", type=int, default=16, help="frames per host-buffer call")
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--cpu-baseline-frames", type=int, default=12)
+    ap.add_argument("--gpu-baseline-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg)
         return
     if args.warmup < 3:
         args.warmup = 3
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    from faster_rcnn_pytorch_multimodal_b200 import _lib, ops
-    from faster_rcnn_pytorch_multimodal_b200.layer_utils.snippets import generate_anchors_pre
-    L = _lib.lib()
-    cfg, F = CFG, args.frames
-    A, P = cfg["A"], cfg["pooled"]
-    n_loc = cfg["Hf"] * cfg["Wf"]
-    anchors, _ = generate_anchors_pre(cfg["Hf"], cfg["Wf"], cfg["stride"], SCALES, RATIOS, 1.0, device=dev)
-    prob, deltas, feat, info = synth_frames(cfg, F, dev, first_frame=rank * F)
-    M = cfg["post_nms"]
-    pooled = torch.empty(F * M, cfg["C"], P, P, device=dev)
-
-    def step(timed_events=None):
-        rois, scores, _, _, num = ops.proposal_batched(prob, deltas, info, anchors, None, A, cfg["pre_nms"],
-                                                       cfg["post_nms"], cfg["nms_thresh"], batch_index_stride=1)
-        if timed_events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        ops._roi_align_forward(feat, rois.view(-1, 5), (P, P), 1.0 / cfg["stride"], cfg["sampling_ratio"], False,
-                               seg_count=num, seg_stride=M, out=pooled)
-        if timed_events is not None:
-            e1.record()
-            timed_events.append((e0, e1))
-        return rois, scores, num
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        rois, scores, num = step()
-    if dist is not None:          # warm the communicator: the first NCCL collective builds its channels
-        rec = torch.cat((rois.view(F, -1), scores, num.view(F, 1).float()), dim=1)
-        dist.all_gather([torch.empty_like(rec) for _ in range(world)], rec)
-    barrier()
-    crop_events = []
-    wall0 = time.perf_counter()
-    launches0 = L.b2d_launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        rois, scores, num = step(crop_events)
-    if dist is not None:
-        # end-of-stream gather of the detection records (the path's only collective)
-        rec = torch.cat((rois.view(F, -1), scores, num.view(F, 1).float()), dim=1)
-        gathered = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(gathered, rec)
-    t_end.record()
-    barrier()
-    wall1 = time.perf_counter()
-    launches = L.b2d_launch_count() - launches0
-    elapsed_ms = t_start.elapsed_time(t_end)
-    crop_ms = float(np.mean([a.elapsed_time(b) for a, b in crop_events]))
-    if dist is not None:
-        t = torch.tensor([elapsed_ms, crop_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, crop_ms = float(t[0]), float(t[1])
-    n_rois = int(num.sum().item())
-    value = world * F * args.steps / (elapsed_ms * 1e-3)
-
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
-    Fe = max(1, min(args.e2e_frames, F))
-    h = lambda t: t.cpu().pin_memory()
-    hp, hd, hf, hi = h(prob[:Fe]), h(deltas[:Fe]), h(feat[:Fe]), h(info[:Fe])
-    o_rois = torch.empty(Fe, M, 5).pin_memory()
-    o_sc = torch.empty(Fe, M).pin_memory()
-    o_num = torch.empty(Fe, dtype=torch.int32).pin_memory()
-    o_pool = torch.empty(Fe * M, cfg["C"], P, P).pin_memory()
-    ws_bytes = L.b2d_pipeline_device_bytes(Fe, n_loc, A, cfg["C"], cfg["Hf"], cfg["Wf"], cfg["pre_nms"], M, P)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-
-    def e2e_step():
-        _lib.check(L.b2d_proposal_crop_host(Fe, n_loc, A, cfg["C"], cfg["Hf"], cfg["Wf"], _lib.ptr(hp), _lib.ptr(hd),
-                                            _lib.ptr(hi), _lib.ptr(anchors), _lib.ptr(hf), cfg["pre_nms"], M,
-                                            cfg["nms_thresh"], P, 1.0 / cfg["stride"], cfg["sampling_ratio"],
-                                            _lib.ptr(o_rois), _lib.ptr(o_sc), _lib.ptr(o_num), _lib.ptr(o_pool),
-                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "b2d_proposal_crop_host")
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e_steps = max(3, args.steps // 2)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t[0])
-    e2e_value = world * Fe * e_steps / (e2e_ms * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in (hp, hd, hf, hi))
-    d2h = sum(t.numel() * t.element_size() for t in (o_rois, o_sc, o_num, o_pool))
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    # device and host paths must agree
-    assert torch.equal(o_num, num[:Fe].cpu()) and torch.equal(o_rois, rois[:Fe].cpu())
-
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-        b_prop, b_nms, b_crop = algorithmic_bytes(cfg, n_rois / F)
-        crop_gbs = F * b_crop / (crop_ms * 1e-3) / 1e9
-        step_gbs = F * (b_prop + b_nms + b_crop) / (elapsed_ms / args.steps * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))            # one ncu --set full capture, scaled to this run's frames per launch
-            traffic = tj["dram_bytes_per_launch"] * F / tj["frames_in_launch"]
-        line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "frames_per_step_per_gpu": F, "anchors_per_frame": n_loc * A,
-                       "pre_nms": cfg["pre_nms"], "post_nms": M, "channels": cfg["C"], "pooled": P,
-                       "sampling_ratio": cfg["sampling_ratio"], "rois_per_frame": n_rois / F,
-                       "l2_policy": f"inputs larger than L2 ({F * (b_prop + cfg['C'] * n_loc * 4) / 1e6:.0f} MB read, "
-                                    f"{F * M * cfg['C'] * P * P * 4 / 1e6:.0f} MB written per step)",
-                       "parallelism": f"frame-stream x{world}, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "rows::fwd_kernel<2,true> (RoIAlign forward)", "achieved": crop_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": crop_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": F * b_crop, "kernel_ms": crop_ms,
-                         "kernel_share_of_step": crop_ms / (elapsed_ms / args.steps),
-                         "fused_stage": {"achieved": step_gbs, "frac": step_gbs / peak,
-                                         "algorithmic_bytes_per_frame": b_prop + b_nms + b_crop}},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_call": Fe, "ms_per_call": e2e_ms / e_steps,
-                    "note": "PCIe-bound: 45 MB up and 60 MB down per frame; frames pipelined over H2D / compute / D2H streams"},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            fps, med = cpu_reference_frames_per_s(cfg, args.cpu_baseline_frames, 1, threads)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_baseline_frames} frames of {cfg['name']} after 1 warm-up, "
-                                              f"oracle port of proposal_layer + torchvision roi_align, {threads} threads",
-                                    "median_ms_per_frame": 1e3 * med}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if cfg["kind"] != "inference":
+        args.cpu_baseline_frames = min(args.cpu_baseline_frames, 3)
+    {"inference": run_inference, "train": run_train, "fpn": run_fpn, "mc": run_mc}[cfg["kind"]](args, cfg)
 
 
 if __name__ == "__main__":

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "b2d_mc_variance": (I, [I, I, _f, I, _f, _v]),
     "b2d_mc_class_uncertainty": (I, [I, I, I, _f, _f, _f, _v]),
     "b2d_var_sort": (I, [I, I, _f, I, _f, _i, _v]),
+    "b2d_head_tail_decode": (I, [I, I, I, I, I, _f, _f, _f, _f, _f, _f, C.POINTER(C.c_float), C.POINTER(C.c_float), I, I, I,
+                                 _f, _f, _f, _f, _f, _f, _v]),
     "b2d_bev_workspace_bytes": (SZ, [I, I, I, I]),
     "b2d_bev_rasterize": (I, [I, I, _f, F32, F32, F32, F32, F32, F32, F32, F32, I, I, I, I, I, I, I, _f, _i, _v, SZ, _v]),
     "b2d_final_detections": (I, [I, I, I, I, _f, _f, _i, _f, I, F32, F64, I, I, _f, I, _f, I, _f, _i, _f, _f, _i, _v]),

@@ -40,19 +40,19 @@
 // sorted by first row; warps claim items from a shared counter and prefetch the next record while they
 // compute.
 //
-// Output (the phase that bounds the kernel: a build that computes nothing and only writes the 60 MB of
-// pooled features per frame runs within 3 % of the full kernel).  Only whole [32 ch][49] slices of the
-// output - 6272 contiguous bytes - leave at memory speed; 28-byte runs 196 bytes apart (one bin-row of 32
-// channels) cost five times as much per byte on the store path.  So EVERY RoI leaves as a whole slice:
-//   * a RoI that is ONE item (all sample rows inside the window): the warp try-locks one of kPool shared
-//     tiles, writes its 49 values per lane there and ONE bulk copy (cp.async.bulk shared -> global) stores
-//     the slice;
-//   * a RoI split over several windows: each item stores its bin-rows TRANSPOSED, [bin][32 ch], into the
-//     RoI's own output slice - fully coalesced 128-byte stores, the slice doubles as the assembly buffer and
-//     stays in L2 - and counts itself done on a per-RoI shared-memory counter; the warp that completes the
-//     count reads the slice back (L2), transposes it through a pool tile and bulk-stores it in place.
-// Ragged channel groups, unaligned outputs and the cp.async variant stage one bin-row [32 ch][7] at a time
-// so that global stores run along (c, pw).
+// Output.  A whole-RoI item (nph = 7) of a full channel group is 6272 contiguous bytes of the output:
+// the warp try-locks one of kPool shared tiles, writes its 49 values per lane there and ONE bulk copy
+// (cp.async.bulk shared -> global) stores the slice - no LDS/STG round trip, half of all output bytes on
+// the bench workload.  Everything else (items of RoIs split over several windows, ragged channel groups,
+// the cp.async variant) is staged one bin-row [32 ch][7] at a time so that global stores run along (c, pw).
+// Measured and rejected (round 2, B200, 64 frames): assembling split RoIs in their own output slice - every
+// item stores its bin-rows transposed [bin][32 ch] with fully coalesced 128-byte stores, a per-RoI shared
+// counter elects the last item, which reads the slice back from L2, transposes it through a pool tile and
+// bulk-stores it in place.  The coalesced part stores alone run at 34.5 us/frame against 36.7 for the
+// bin-row path, but the __threadfence() that must precede the count costs 7 us (it waits for the stores the
+// warp has just issued) and the read-back + transpose 17-24 us (49 dependent L2 loads stall one of only 8
+// consumer warps): 66 us/frame in total.  The scattered bin-row stores cost 2 us, not the 12 the round-1
+// knock-out build suggested; what the kernel waits for is the shared-memory pipe (0.7 wavefronts/clk).
 //
 // Two things ptxas must be told (each cost 10 % when missed): (1) every branch on a warp-uniform value
 // goes through a warp reduction (CREDUX -> uniform register); one branch it takes for divergent - the
@@ -74,7 +74,7 @@ namespace rows {
 #define B2D_STAGES 2
 #endif
 #ifndef B2D_POOL
-#define B2D_POOL 3
+#define B2D_POOL 2
 #endif
 #ifndef B2D_SLACK
 #define B2D_SLACK 2
@@ -91,7 +91,6 @@ constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each takes the RoIs e % split == part
-constexpr int kMaxCount = 4096;    // RoIs per frame the per-RoI completion counters cover (one byte each)
 
 constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps
 constexpr int kTileWords = kCh * kP * kP;
@@ -103,7 +102,6 @@ struct Plan {
   int lane_stride;  // words between channels of one slot (odd)
   int row_words;    // words per ring slot
   int Rr, St, nblk, nbk, span_max, span_whole, nsteps;
-  int cnt_bytes;    // per-RoI completion counters (0: split RoIs take the bin-row store path)
   size_t smem;
   bool ok;
 };
@@ -113,7 +111,7 @@ struct Plan {
 // with that per-row shift.
 static int stage_width(int W) { return W % 4 == 0 ? W : (W + 3) / 4 * 4 + 4; }
 
-static Plan make_plan(int H, int W, int per_frame, bool allow_tma) {
+static Plan make_plan(int H, int W, bool allow_tma) {
   Plan p{};
   p.fill = (allow_tma && (H * W) % 4 == 0 && stage_width(W) <= 256) ? 1 : 0;
   const int pitch = (W + 1) | 1;                     // smallest ODD value >= W + 1: any odd pitch maps 32 channels to 32 banks
@@ -123,8 +121,7 @@ static Plan make_plan(int H, int W, int per_frame, bool allow_tma) {
   const size_t staging = p.fill ? (size_t)kStages * kCh * stage_width(W) * 4 : 0;
   const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and a bin-row tile
   const size_t pool = p.fill ? (size_t)kPool * kTileWords * 4 : 0;
-  p.cnt_bytes = (p.fill && per_frame <= kMaxCount) ? (int)align_up((size_t)per_frame, 16) : 0;
-  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * kCh * kP * 4 + 256 + staging + pool + p.cnt_bytes;
+  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * kCh * kP * 4 + 256 + staging + pool;
   const size_t budget = 227 * 1024 - 1280;       // 1.2 KB of static shared memory (barriers, locks, counters)
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
@@ -232,7 +229,7 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 
 // Record of one item (float4 units):
 //   [0]       {roi row r, ph0 | nph << 4 | nrows << 8 | slow << 16, block of the first row (bucket) | block of the
-//              last row << 16, index of the RoI in its frame's list | items of the RoI << 24}
+//              last row << 16, 0}
 //   [1..11]   14 column taps: 14 byte offsets of the lo column (the hi column is lo + 1), then the weights;
 //             S == 2: per bin pair (2j, 2j+1) the weights of tap a / b of the first sample and c / d of the second
 //             as aligned register pairs, then bin 6;  S == 1: {offset, hx, lx} triples
@@ -293,8 +290,6 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
     const float inv_cnt = 1.0f / g.count;
     const int part = i % split;
-    int n_items = 0;
-    for_each_item<S>(g, H, span_max, span_whole, [&](int, int, int, int, bool) { ++n_items; });
     // column taps (the same for every item of the RoI).  Invalid samples carry zero weights and point at
     // column 0 (always resident); at the clamped right border lx is 0 and the hi tap reads whatever follows
     // the row (finite).
@@ -371,8 +366,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
       }
       const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
       const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
-      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks),
-                           __int_as_float((i & 0xFFFFFF) | (n_items << 24)));
+      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks), 0.0f);
     });
   }
 }
@@ -427,11 +421,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Output tile pool of the TMA variant: kPool tiles [32 ch][49].  A warp with a whole slice to store TRIES to
-// take a tile (one pass over the locks, no waiting - a warp that blocked here would stop publishing its
-// progress and could starve the fill the tile holders are waiting on): with a tile the 49 values of each lane
-// go to shared memory once and leave with ONE bulk store of 6272 contiguous bytes; the tile stays locked until
-// the copy has read it (released at the warp's next item).
+// Output tile pool of the TMA variant: kPool whole-RoI tiles [32 ch][49].  A whole-RoI item of a full channel
+// group TRIES to take a tile (one pass over the locks, no waiting - a warp that blocked here would stop
+// publishing its progress and could starve the fill the tile holders are waiting on): with a tile the 49 values
+// of each lane go to shared memory once and leave with ONE bulk store of 6272 contiguous bytes; the tile stays
+// locked until the copy has read it (released at the warp's next item).  Without one the item takes the
+// bin-row path.
 __device__ __forceinline__ int tile_try_acquire(int* locks, int warp, int lane) {
   unsigned t = 0;                          // tile index + 1, 0 = none
   if (lane == 0) {
@@ -460,14 +455,10 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 // One item: nph = NPH bin-rows of one RoI for this lane's channel.
 // NPH is the variant (2, 4 or 7 accumulator rows), nph <= NPH the bin-rows the item really has: the rows in
 // between carry zero weights and are not stored.
-//   part != nullptr : the RoI has several items -> bin-rows go, transposed, to part[(p*7 + pw)*32] (lane-major,
-//                     128-byte coalesced stores); the caller counts the item done afterwards
-//   else            : whole-RoI item -> pool tile + one bulk store if a tile is free, otherwise (and for ragged
-//                     groups / the cp.async variant) one bin-row [32 ch][7] at a time through `stage`
 template <int NPH, int S, bool POOL>
 __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
-                                         float* __restrict__ part, const int (&ooff)[kP], unsigned omask,
+                                         const int (&ooff)[kP], unsigned omask,
                                          float* __restrict__ pool, int* locks, int warp, bool tile_out, int& held) {
   constexpr int NX = kP * S;
   constexpr int RV = NPH > 2 ? 2 : 1;
@@ -606,16 +597,6 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
   return;      // A/B timing build: results discarded
 #endif
   if (POOL) {
-    if (part != nullptr) {
-      // one item of a split RoI: bin-rows transposed into the RoI's slice, 128 bytes per store
-#pragma unroll
-      for (int p = 0; p < NPH; ++p) {
-        if (p >= nph) break;
-#pragma unroll
-        for (int pw = 0; pw < kP; ++pw) part[(p * kP + pw) * kCh] = B2D_ACC(p, pw);
-      }
-      return;
-    }
     if (NPH == kP && kPool > 0 && tile_out && nph == kP) {
       const int t = tile_try_acquire(locks, warp, lane);
       if (t >= 0) {
@@ -653,7 +634,7 @@ struct KArgs {
   RoiList L;
   int C, H, W;
   int lane_stride, row_words, stage_w;
-  int St, nblk, nbk, nsteps, items_cap, cnt_bytes;
+  int St, nblk, nbk, nsteps, items_cap;
   Ws ws;
   float* out;
 };
@@ -683,7 +664,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const int St = a.St, nblk = a.nblk, nsteps = a.nsteps;
   const int row_words = a.row_words;
   const float* fbase = feat_g + ((size_t)f * C + c0) * H * W;
-  // dynamic shared: [ring (128-byte aligned)][record slots][bin-row tiles][pool][staging][counters]
+  // dynamic shared: [ring (128-byte aligned)][record slots][bin-row tiles][pool][staging]
   // (pointer arithmetic on `smem` keeps the shared address space; a cast through an integer would
   // turn every slot / staging access into a generic load)
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
@@ -691,7 +672,6 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * kCh * kP;
   float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * kCh * kP;
   float* stg = pool + (FILL ? (size_t)kPool * kTileWords : 0);
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(stg + (FILL ? (size_t)kStages * kCh * a.stage_w : 0));   // one byte per RoI of the frame
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
   if (tid < kPool) s_tile_lock[tid] = 0;
@@ -703,7 +683,6 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       mbar_init(&done_bar[i], kConsumers);
     }
   }
-  for (int i = tid; i < a.cnt_bytes / 4; i += kThreads) s_cnt[i] = 0u;
   {
     // pad columns x in [W, pitch) are read by clamped taps with weight 0: keep them finite
     const int pitch = a.lane_stride, padw = pitch - W;
@@ -795,14 +774,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const uint32_t lane_base = ring_s + (uint32_t)lane * (uint32_t)a.lane_stride * 4u;
   // bulk stores need 16-byte aligned RoI slices: C * 49 * 4 bytes per RoI -> C % 4 == 0
   const bool tile_out = FILL && nch == kCh && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out_g) & 15u) == 0;
-#ifdef B2D_AB_NOSTORE
-  const bool parts_on = false;
-#else
-  const bool parts_on = tile_out && a.cnt_bytes > 0;    // split RoIs are assembled in their own output slice
-#endif
   int held = -1;        // pool tile a bulk store of this warp may still be reading
-  int pend_e = -1;      // split RoI whose item this warp has just stored (counted done at the next item)
-  int pend_r = 0, pend_n = 0;
   const float4* recs = records_g + (size_t)f * a.items_cap * kRecVec;
   const int item0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part]);
   const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part + 1]);
@@ -883,46 +855,15 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     }
     cur = max(cur, to);
   };
-  // Between items: give back the pool tile of the previous bulk store, then count the previous split item
-  // done; the warp that completes a RoI's count turns the assembled slice [49 bins][32 ch] (written by this
-  // CTA's warps, L2-resident) into the final [32 ch][49] layout, in place.
+  // Between items: give back the pool tile of the previous bulk store.
   auto between_items = [&]() {
-    // (`held` / `pend_e` are warp-uniform; the reductions tell ptxas so - a branch it takes for divergent
-    // costs the consumers their [column + uniform row] tap addressing)
+    // (`held` is warp-uniform; the reduction tells ptxas so - a branch it takes for divergent costs the
+    // consumers their [column + uniform row] tap addressing)
     if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
       // the bulk store issued by the previous item has (nearly always) read its tile by now
       if (lane == 0) bulk_wait_read();
       tile_release(s_tile_lock, held, lane);
       held = -1;
-    }
-    if (FILL && __reduce_max_sync(0xffffffffu, (unsigned)(pend_e + 1)) != 0u) {
-      __threadfence();                          // this warp's part stores are performed before it is counted
-      __syncwarp();
-      unsigned old = 0u;
-      if (lane == 0) old = atomicAdd(&s_cnt[pend_e >> 2], 1u << (8 * (pend_e & 3)));
-      old = (__reduce_max_sync(0xffffffffu, old) >> (8 * (pend_e & 3))) & 0xFFu;
-      if ((int)old + 1 == pend_n) {
-        __threadfence();                        // acquire: every other item's stores are visible
-        float* slice = out_g + ((size_t)pend_r * C + c0) * bins;
-        float v[bins];
-#pragma unroll
-        for (int k = 0; k < bins; ++k) v[k] = __ldcg(slice + k * kCh + lane);
-        const int t = tile_try_acquire(s_tile_lock, warp, lane);
-        if (__reduce_max_sync(0xffffffffu, (unsigned)(t + 1)) != 0u) {
-          float* tile = pool + (size_t)t * kTileWords;
-#pragma unroll
-          for (int k = 0; k < bins; ++k) tile[lane * bins + k] = v[k];
-          asm volatile("fence.proxy.async;" ::: "memory");   // tile writes (shared) and the slice's earlier generic writes (global) before the bulk copy
-          __syncwarp();
-          if (lane == 0) bulk_s2g(slice, smem_u32(tile), (uint32_t)kTileWords * 4u);
-          held = t;
-        } else {
-          __syncwarp();                         // every lane has read the whole slice before any lane overwrites it
-#pragma unroll
-          for (int k = 0; k < bins; ++k) slice[lane * bins + k] = v[k];
-        }
-      }
-      pend_e = -1;
     }
   };
   pump();
@@ -944,25 +885,15 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int r = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.x));
     const int code = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.y));
     const int blocks = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
-    const int ent = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.w));
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
     const int bucket = blocks & 0xFFFF, last_blk = blocks >> 16;
-    const int roi_items = ent >> 24;
     float* o = out_g + ((size_t)r * C + c0) * bins + ph0 * kP;
-    // items of a split RoI store into the transposed slice and are counted
-    const bool is_part = parts_on && roi_items > 1;
-    float* part_dst = is_part ? out_g + ((size_t)r * C + c0) * bins + (size_t)ph0 * kP * kCh + lane : nullptr;
-    if (is_part) {
-      pend_e = ent & 0xFFFFFF;
-      pend_r = r;
-      pend_n = roi_items;
-    }
     if (!((code >> 16) & 1)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       // (only the blocks the item reads have to be there, not its whole window)
       release(bucket);
       observe(min(last_blk + 1, nsteps));
-#define B2D_RUN(N) run_item<N, S, FILL>(slot, nrows, nph, lane_base, stage, lane, o, part_dst, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
+#define B2D_RUN(N) run_item<N, S, FILL>(slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
       if (nph <= 2) B2D_RUN(2);
       else if (nph <= 4) B2D_RUN(4);
       else B2D_RUN(7);
@@ -987,8 +918,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
           }
         }
 #ifndef B2D_AB_NOSTORE
-        if (is_part) part_dst[pw * kCh] = acc / g.count;
-        else if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
+        if (ch_ok) o[(size_t)lane * bins + pw] = acc / g.count;
 #endif
       }
     }
@@ -997,11 +927,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   }
   // out of items: release every remaining bucket so the fill can finish
   release(nsteps);
-  between_items();      // count the last split item (and possibly assemble its RoI)
-  if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {   // the last bulk store still reads shared memory
-    if (lane == 0) bulk_wait_read();
-    tile_release(s_tile_lock, held, lane);
-  }
+  between_items();      // the last bulk store still reads shared memory
   if (!FILL) {
     while (issued < nsteps) pump();
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1050,7 +976,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   const int per_frame = L.seg_count ? L.seg_stride : L.n;
-  const Plan p = make_plan(H, W, per_frame, !coop_fill && make_tmap(&tmap, feat, F, C, H, W));
+  const Plan p = make_plan(H, W, !coop_fill && make_tmap(&tmap, feat, F, C, H, W));
   if (!p.ok || p.nsteps >= 0xFFFF) return B2D_ERR_UNSUPPORTED;
   Ws ws = carve(workspace, F, per_frame);
   if (!workspace || workspace_bytes < ws.bytes) return B2D_ERR_UNSUPPORTED;
@@ -1067,7 +993,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   while (split < kMaxSplit && groups * split < 2 * kNumSMs) split *= 2;
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
-  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, p.cnt_bytes, ws, out};
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
     prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * split * nb, st>>>(                        \

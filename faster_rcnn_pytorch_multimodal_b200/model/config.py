@@ -29,6 +29,9 @@ __C.USE_FPN = False                          # config.py:51
 __C.RNG_SEED = 3                             # config.py:346
 __C.POOLING_MODE = 'align'                   # config.py:364
 __C.POOLING_SIZE = 7                         # config.py:367
+# RoIAlign samples per bin and axis.  Not a key of the reference's config: its value lives in the missing
+# lib/nets/network.py; 2 is the upstream default the fork descends from.  <= 0 = adaptive.
+__C.POOLING_SAMPLING_RATIO = 2
 __C.ANCHOR_SCALES = [2, 4, 8, 16, 32]        # config.py:373
 __C.ANCHOR_RATIOS = [0.5, 0.75, 1, 1.25, 2]  # config.py:378
 

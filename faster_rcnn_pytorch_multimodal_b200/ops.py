@@ -314,3 +314,55 @@ def final_detections(cls_score, pred_boxes, info, num_elem, db_type, score_thres
                                      ptr(ucl), n_uc, ptr(dets), ptr(det_roi), ptr(o_ur), ptr(o_uc), ptr(counts),
                                      stream_ptr(dev)), "b2d_final_detections")
     return dets, det_roi, counts, o_ur, o_uc
+
+
+# ------------------------------------------------------------------------------------------
+# Tail of the detection head over the MC-dropout stack, one launch for all frames
+# ------------------------------------------------------------------------------------------
+def head_tail_decode(bbox_pred, cls_score, rois, anchors_3d, info, net_type, a_bbox_var=None, use_scale=False,
+                     clip=True, means=None, stds=None):
+    """bbox_pred [T,F,R,K*E] (normalised deltas of T stacked head passes), cls_score [T,F,R,K], rois [F,R,5],
+    anchors_3d [F,R,7] (lidar), info [F,7] -> dict, every tensor in ``final_detections``' input layout:
+
+      boxes [F,R,K*E]        de-normalised (model/config.py:219-223) mean prediction, decoded with
+                             lidar_3d_bbox_transform_inv / bbox_transform_inv + clip_boxes
+      probs [F,R,K]          mean softmax
+      e_bbox_var [F,R,K*E]   compute_bbox_var of the de-normalised samples through lidar_3d_uncertainty_transform_inv
+      a_bbox_var [F,R,K*E]   the same transform of the aleatoric head output (only when ``a_bbox_var`` is given)
+      e_entropy, e_mutual_info [F,R]   utils/loss_utils.py:122-141
+
+    T = 1 (no MC-dropout) gives the plain decode with zero epistemic variance.  ``means`` / ``stds`` default to
+    ``cfg.TRAIN.{LIDAR,IMAGE}.BBOX_NORMALIZE_{MEANS,STDS}``."""
+    import ctypes as C
+    from .model.config import cfg
+    require_cuda(bbox_pred, cls_score, rois, anchors_3d, info, a_bbox_var)
+    lidar = net_type == "lidar"
+    E = 7 if lidar else 4
+    bp, cs, ro, inf = f32c(bbox_pred), f32c(cls_score), f32c(rois), f32c(info)
+    if bp.dim() == 3:                      # [F,R,K*E]: a single head pass
+        bp, cs = bp.unsqueeze(0), cs.unsqueeze(0)
+    T, F, R, KE = bp.shape
+    K = cs.shape[3]
+    if KE != K * E or cs.shape[:3] != (T, F, R) or ro.shape != (F, R, 5) or inf.shape != (F, 7):
+        raise _lib.B2DError("head_tail_decode: shape mismatch")
+    if lidar and (anchors_3d is None or tuple(anchors_3d.shape) != (F, R, 7)):
+        raise _lib.B2DError("head_tail_decode: lidar needs anchors_3d [F,R,7]")
+    a3 = f32c(anchors_3d) if anchors_3d is not None else None
+    av = f32c(a_bbox_var) if a_bbox_var is not None else None
+    tr = cfg.TRAIN.LIDAR if lidar else cfg.TRAIN.IMAGE
+    means = list(tr.BBOX_NORMALIZE_MEANS if means is None else means)
+    stds = list(tr.BBOX_NORMALIZE_STDS if stds is None else stds)
+    if len(means) != E or len(stds) != E:
+        raise _lib.B2DError("head_tail_decode: means / stds need one value per box element")
+    dev = bp.device
+    out = {"boxes": torch.empty(F, R, KE, device=dev), "probs": torch.empty(F, R, K, device=dev),
+           "e_bbox_var": torch.empty(F, R, KE, device=dev), "e_entropy": torch.empty(F, R, device=dev),
+           "e_mutual_info": torch.empty(F, R, device=dev)}
+    if av is not None:
+        out["a_bbox_var"] = torch.empty(F, R, KE, device=dev)
+    check(lib(dev).b2d_head_tail_decode(F, T, R, K, E, ptr(bp), ptr(cs), ptr(ro), ptr(a3), ptr(inf), ptr(av),
+                                        (C.c_float * E)(*means), (C.c_float * E)(*stds), 1 if lidar else 0,
+                                        int(bool(use_scale)), int(bool(clip)), ptr(out["boxes"]), ptr(out["probs"]),
+                                        ptr(out["e_bbox_var"]), ptr(out.get("a_bbox_var")), ptr(out["e_entropy"]),
+                                        ptr(out["e_mutual_info"]), stream_ptr(dev)), "b2d_head_tail_decode")
+    return out

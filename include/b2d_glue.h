@@ -268,6 +268,30 @@ int b2d_mc_class_uncertainty(int num_samples, int n, int num_classes, const floa
 int b2d_var_sort(int n, int cols, const float* var, int descending, float* key, int32_t* order, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Tail of the detection head over the MC-dropout stack, ONE launch for all frames.
+ * Restates, element by element: per-class de-normalisation `bbox_pred * stds + means`  model/config.py:219-223;
+ * the mean over the T samples and compute_bbox_var  utils/loss_utils.py:114-120;
+ * lidar_3d_bbox_transform_inv  model/bbox_transform.py:174-233 (mode 1) or bbox_transform_inv + clip_boxes
+ * :75-105,235-257 (mode 0); lidar_3d_uncertainty_transform_inv  :132-169 on the epistemic variance and on an
+ * optional aleatoric variance input; softmax + mean class probability, categorical_entropy and
+ * categorical_mutual_information  utils/loss_utils.py:122-141.  (Network.test_frame, which strings these
+ * together, is in the missing lib/nets/network.py: the composition is [INFERRED])
+ *   bbox_pred [T, F, R, K*E], cls_score [T, F, R, K]: T head passes over the same F*R RoIs, stacked;
+ *   rois [F, R, 5]; anchors_3d [F, R, 7] (mode 1); info [F, 7]; a_bbox_var_in [F, R, K*E] or NULL;
+ *   means_host / stds_host [E]: HOST arrays (copied into the launch);
+ *   use_scale: divide the RoIs by info[f][6] first; clip (mode 0): clip_boxes to info.
+ * Outputs, in b2d_final_detections' input layout: boxes [F, R, K*E]; probs [F, R, K];
+ *   e_bbox_var [F, R, K*E] (0 when T == 1) or NULL; a_bbox_var [F, R, K*E] or NULL; entropy [F, R] or NULL;
+ *   mutual_info [F, R] or NULL.  mode 0 returns raw variances (the reference's image flavour of the
+ *   uncertainty transform is unusable).  K <= 16.
+ * ---------------------------------------------------------------------------------- */
+int b2d_head_tail_decode(int num_frames, int num_samples, int num_rois, int num_classes, int num_elem,
+                         const float* bbox_pred, const float* cls_score, const float* rois, const float* anchors_3d,
+                         const float* info, const float* a_bbox_var_in, const float* means_host,
+                         const float* stds_host, int mode, int use_scale, int clip, float* boxes, float* probs,
+                         float* e_bbox_var, float* a_bbox_var, float* entropy, float* mutual_info, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * LiDAR BEV rasterisation for one frame of points.
  * Replaces the CPU path of _get_lidar_blob()  roi_data_layer/minibatch.py:428-512:
  *   filter_points() :232-235, z shift :454, spconv.utils.VoxelGeneratorV2.generate() :445-456

@@ -346,9 +346,65 @@ def gen_bev():
     print("bev.npz", os.path.getsize(os.path.join(OUT, "bev.npz")))
 
 
+def gen_head_tail():
+    """tests/golden/head_tail.npz: the tail of the detection head over T MC-dropout passes,
+    composed from the UNMODIFIED reference functions - de-normalisation with cfg.TRAIN.*.BBOX_NORMALIZE_* (config.py:
+    219-223), torch.mean, compute_bbox_var, lidar_3d_bbox_transform_inv / bbox_transform_inv + clip_boxes,
+    lidar_3d_uncertainty_transform_inv, softmax mean, categorical_entropy, categorical_mutual_information.
+    (The method that strings them together, Network.test_frame, is in the missing lib/nets/network.py.)"""
+    R = ref_import.load()
+    g = torch.Generator().manual_seed(SEED + 40)
+    out = {}
+    T, F, n, K = 6, 2, 37, 3
+    for tag, E in (("lidar", 7), ("image", 4)):
+        tr = R.cfg.TRAIN.LIDAR if tag == "lidar" else R.cfg.TRAIN.IMAGE
+        stds = torch.tensor(tr.BBOX_NORMALIZE_STDS, dtype=torch.float32).repeat(K)
+        means = torch.tensor(tr.BBOX_NORMALIZE_MEANS, dtype=torch.float32).repeat(K)
+        mu = torch.randn(F, n, K * E, generator=g)
+        bbox = mu.unsqueeze(0) + 0.1 * torch.randn(T, F, n, K * E, generator=g)
+        cls = 2.0 * torch.randn(F, n, K, generator=g).unsqueeze(0) + 0.4 * torch.randn(T, F, n, K, generator=g)
+        xy = torch.rand(F, n, 2, generator=g) * torch.tensor([600.0, 700.0])
+        wh = torch.rand(F, n, 2, generator=g) * 70 + 6
+        rois = torch.cat((torch.arange(F).view(F, 1, 1).expand(F, n, 1).float(), xy, xy + wh), 2)
+        a3d = torch.tensor([0, 0, 0.885, 47.3, 20.8, 1.77, 0.0]).repeat(F, n, 1) + 0.05 * torch.randn(F, n, 7, generator=g)
+        a_var = 0.02 * torch.rand(F, n, K * E, generator=g)
+        info = torch.tensor([[0, 700.0, 0, 800.0, 0, 12.0, 1.0], [0, 700.0, 0, 800.0, 0, 12.0, 1.25]])
+        res = {k: [] for k in ("boxes", "boxes_scaled", "e_var", "a_var", "probs", "ent", "mi")}
+        for f in range(F):
+            x = bbox[:, f] * stds + means                                   # config.py:219-223
+            mean_pred = torch.mean(x, dim=0)
+            var = R.lu.compute_bbox_var(x)
+            if tag == "lidar":
+                res["boxes"].append(R.bt.lidar_3d_bbox_transform_inv(rois[f, :, 1:5], a3d[f].clone(), mean_pred))
+                res["boxes_scaled"].append(R.bt.lidar_3d_bbox_transform_inv(rois[f, :, 1:5], a3d[f].clone(), mean_pred,
+                                                                            scales=float(info[f, 6])))
+                res["e_var"].append(R.bt.lidar_3d_uncertainty_transform_inv(rois[f, :, 1:5], a3d[f].clone(), mean_pred, var))
+                res["a_var"].append(R.bt.lidar_3d_uncertainty_transform_inv(rois[f, :, 1:5], a3d[f].clone(), mean_pred,
+                                                                            a_var[f]))
+            else:
+                res["boxes"].append(R.bt.clip_boxes(R.bt.bbox_transform_inv(rois[f, :, 1:5], mean_pred), info[f].numpy()))
+                res["boxes_scaled"].append(R.bt.clip_boxes(
+                    R.bt.bbox_transform_inv(rois[f, :, 1:5], mean_pred, scales=float(info[f, 6])), info[f].numpy()))
+                res["e_var"].append(var)
+                res["a_var"].append(a_var[f])
+            probs = torch.mean(torch.softmax(cls[:, f], dim=2), dim=0)
+            res["probs"].append(probs)
+            res["ent"].append(R.lu.categorical_entropy(probs))
+            res["mi"].append(R.lu.categorical_mutual_information(cls[:, f]))
+        out.update({f"{tag}_bbox": _np(bbox), f"{tag}_cls": _np(cls), f"{tag}_rois": _np(rois), f"{tag}_a3d": _np(a3d),
+                    f"{tag}_a_var_in": _np(a_var), f"{tag}_info": _np(info), f"{tag}_stds": _np(stds[:E]),
+                    f"{tag}_means": _np(means[:E])})
+        out.update({f"{tag}_{k}": _np(torch.stack(v)) for k, v in res.items()})
+    np.savez_compressed(os.path.join(OUT, "head_tail.npz"), **out)
+    print("head_tail.npz", os.path.getsize(os.path.join(OUT, "head_tail.npz")))
+
+
 if __name__ == "__main__":
     if "--only-bev" in sys.argv:
         sys.exit(gen_bev())
+    if "--only-head-tail" in sys.argv:
+        sys.exit(gen_head_tail())
     rc = main()
     gen_bev()
+    gen_head_tail()
     sys.exit(rc)

@@ -839,3 +839,44 @@ def filter_detections(cls_score: torch.Tensor, pred_boxes: torch.Tensor, info, n
                       uc_cls=None if uc_cls is None else
                       uc_cls.numpy()[roi][:, :, j * bbox_elem:(j + 1) * bbox_elem])
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Tail of the detection head over the MC-dropout stack
+# --------------------------------------------------------------------------------------
+def head_tail_decode(bbox_pred: torch.Tensor, cls_score: torch.Tensor, rois: torch.Tensor, anchors_3d, info,
+                     net_type: str, a_bbox_var: Optional[torch.Tensor] = None, use_scale: bool = False,
+                     cfg: GlueCfg = DEFAULT_CFG):
+    """One frame: bbox_pred [T,R,K*E], cls_score [T,R,K], rois [R,5] -> dict of the tensors the final per-class filter
+    consumes.  The composition is [INFERRED] (Network.test_frame is in the missing lib/nets/network.py); each step is
+    the reference's: de-normalisation config.py:219-223, torch.mean, compute_bbox_var loss_utils.py:114-120, the
+    decoders bbox_transform.py:75-105,174-233,235-257, lidar_3d_uncertainty_transform_inv :132-169, softmax mean,
+    categorical_entropy / categorical_mutual_information loss_utils.py:122-141."""
+    lidar = net_type == "lidar"
+    E = 7 if lidar else 4
+    K = bbox_pred.shape[2] // E
+    stds = torch.tensor(cfg.lidar_stds if lidar else cfg.image_stds, dtype=torch.float32).repeat(K)
+    means = torch.tensor(cfg.lidar_means if lidar else cfg.image_means, dtype=torch.float32).repeat(K)
+    info = np.asarray(info, dtype=np.float32)
+    x = bbox_pred * stds + means
+    mean_pred = torch.mean(x, dim=0)
+    T = x.shape[0]
+    var = compute_bbox_var(x) if T > 1 else torch.zeros_like(mean_pred)
+    sc = float(info[6]) if use_scale else None
+    out = {}
+    if lidar:
+        out["boxes"] = lidar_3d_bbox_transform_inv(rois[:, 1:5], anchors_3d.clone(), mean_pred, scales=sc)
+        out["e_bbox_var"] = lidar_3d_uncertainty_transform_inv(rois[:, 1:5], anchors_3d.clone(), mean_pred, var, scales=sc)
+        if a_bbox_var is not None:
+            out["a_bbox_var"] = lidar_3d_uncertainty_transform_inv(rois[:, 1:5], anchors_3d.clone(), mean_pred,
+                                                                   a_bbox_var, scales=sc)
+    else:
+        out["boxes"] = clip_boxes(bbox_transform_inv(rois[:, 1:5], mean_pred, scales=sc), info)
+        out["e_bbox_var"] = var
+        if a_bbox_var is not None:
+            out["a_bbox_var"] = a_bbox_var
+    probs = torch.mean(torch.softmax(cls_score, dim=2), dim=0)
+    out["probs"] = probs
+    out["e_entropy"] = categorical_entropy(probs)
+    out["e_mutual_info"] = categorical_mutual_information(cls_score)
+    return out

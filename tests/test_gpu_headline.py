@@ -107,10 +107,11 @@ def test_rows_kernel_at_the_bench_configuration_vs_torchvision():
         assert torch.equal(got_rep[:, g * 32:(g + 1) * 32], ref13), g
 
 
-def test_rows_kernel_split_rois_every_item_count():
+def test_rows_kernel_split_rois_every_item_count(monkeypatch):
     """RoIs from 1 to 70 feature rows tall (1..7 items each, incl. bin-rows taller than the window) on the 80x120
     ring, mixed with small ones, F = 3 with ragged counts: the assembled slices must equal torchvision's."""
     from faster_rcnn_pytorch_multimodal_b200 import ops
+    monkeypatch.setattr(ops, "ROI_ROUTE", "rows")        # (the automatic dispatch sends calls this small to the gather kernel)
     F, C, H, W, M = 3, 64, 80, 120, 120
     g = torch.Generator().manual_seed(17)
     feat = torch.randn(F, C, H, W, generator=g)
@@ -137,9 +138,10 @@ def test_rows_kernel_split_rois_every_item_count():
     assert torch.allclose(got2, want2, rtol=1e-5, atol=1e-5)
 
 
-def test_roi_align_rejects_nothing_silently_int64_counts_and_half_features():
+def test_roi_align_int64_counts_and_half_features(monkeypatch):
     """seg_count given as int64 is converted (the kernels read int32); half features come back as half."""
     from faster_rcnn_pytorch_multimodal_b200 import ops
+    monkeypatch.setattr(ops, "ROI_ROUTE", "rows")
     F, C, H, W, M = 2, 32, 24, 40, 20
     g = torch.Generator().manual_seed(2)
     feat = torch.randn(F, C, H, W, generator=g)
