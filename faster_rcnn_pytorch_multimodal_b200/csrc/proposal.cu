@@ -17,7 +17,8 @@
 namespace b2d {
 
 int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, double thresh, int max_keep,
-                      int32_t* keep, int32_t* num_keep, cudaStream_t st);
+                      int32_t* keep, int32_t* num_keep, void* kept_scratch, cudaStream_t st);
+size_t nms_cluster_workspace_bytes(int F, int max_keep);
 
 struct ProposalWs {
   uint32_t* hist;         // [F][kSelectBins]
@@ -29,8 +30,19 @@ struct ProposalWs {
   int32_t* n_sorted;      // [F]
   int32_t* keep;          // [F][max_out]
   int32_t* num_keep;      // [F]
+  uint32_t* rank;         // [F][kMaxSortElems]: rank-sort counters (few-frame path)
+  void* nms_kept;         // kept boxes of the cluster NMS (few-frame path)
   size_t bytes;
 };
+
+// Few frames per call (the reference API issues ONE): the single-CTA-per-frame bitonic sort leaves 147 SMs idle for
+// 100 us.  Up to kRankMaxFrames frames the candidates are ranked by counting instead, spread over the whole GPU:
+// rank(i) = #{j : composite_j > composite_i} (composites are unique), 3 instructions per pair.
+constexpr int kRankMaxFrames = 8;
+constexpr int kRankThreads = 256;
+constexpr int kRankPerThread = 2;                                  // candidates i per thread
+constexpr int kRankTileI = kRankThreads * kRankPerThread;          // 512 candidates per CTA
+constexpr int kRankTileJ = 512;                                    // compared against 512 candidates per CTA
 
 static int top_k_of(int N, int pre) { return (pre > 0 && pre < N) ? pre : N; }
 static int max_out_of(int N, int pre, int post) {
@@ -58,6 +70,9 @@ static ProposalWs carve(void* base, int F, int N, int pre, int post) {
   w.n_sorted = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
   w.keep = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * mo));
   w.num_keep = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
+  w.rank = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)(F <= kRankMaxFrames ? F : 0) * kMaxSortElems));
+  const size_t nk = nms_cluster_workspace_bytes(F, mo);
+  w.nms_kept = nk ? take(nk) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a, const u
                                                            float* __restrict__ sorted_scores,
                                                            int32_t* __restrict__ sorted_index,
                                                            int32_t* __restrict__ n_sorted, int k_cap,
-                                                           int decode) {
+                                                           int decode, int only_overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
   __shared__ uint32_t hist256[256];
@@ -302,6 +317,7 @@ __global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a, const u
 
   const int f = blockIdx.x;
   const int m = (int)sel[f * 4 + 1];
+  if (only_overflow && m <= kMaxSortElems) return;     // the rank-by-counting kernels sorted this frame
   const int k = min((int)sel[f * 4 + 2], m);
   const uint64_t* cand = cand_all + (size_t)f * a.N;
 
@@ -353,6 +369,84 @@ __global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a, const u
     os[i] = sc;
     oi[i] = idx;
   }
+}
+
+// Rank by counting, few-frame path.  grid (i tiles, j tiles, F); CTAs outside the frame's candidate count leave.
+__global__ void __launch_bounds__(kRankThreads) rank_count_kernel(const uint32_t* __restrict__ sel,
+                                                                  const uint64_t* __restrict__ cand_all, int N,
+                                                                  uint32_t* __restrict__ rank_all) {
+  __shared__ uint64_t s_key[kRankTileJ];
+  const int f = blockIdx.z;
+  const int m = (int)sel[f * 4 + 1];
+  const int i0 = blockIdx.x * kRankTileI, j0 = blockIdx.y * kRankTileJ;
+  if (m > kMaxSortElems || i0 >= m || j0 >= m) return;
+  const uint64_t* cand = cand_all + (size_t)f * N;
+  for (int j = threadIdx.x; j < kRankTileJ; j += kRankThreads) s_key[j] = j0 + j < m ? cand[j0 + j] : 0ull;   // 0 < every key
+  uint64_t mine[kRankPerThread];
+#pragma unroll
+  for (int q = 0; q < kRankPerThread; ++q) {
+    const int i = i0 + q * kRankThreads + threadIdx.x;
+    mine[q] = i < m ? cand[i] : ~0ull;
+  }
+  __syncthreads();
+  uint32_t cnt[kRankPerThread];
+#pragma unroll
+  for (int q = 0; q < kRankPerThread; ++q) cnt[q] = 0u;
+#pragma unroll 8
+  for (int j = 0; j < kRankTileJ; ++j) {
+    const uint64_t kj = s_key[j];
+#pragma unroll
+    for (int q = 0; q < kRankPerThread; ++q) cnt[q] += kj > mine[q] ? 1u : 0u;
+  }
+  uint32_t* rank = rank_all + (size_t)f * kMaxSortElems;
+#pragma unroll
+  for (int q = 0; q < kRankPerThread; ++q) {
+    const int i = i0 + q * kRankThreads + threadIdx.x;
+    if (i < m && cnt[q]) atomicAdd(rank + i, cnt[q]);
+  }
+}
+
+// rank -> position: candidate i goes to row rank[i] of the sorted list (only the first k rows exist);
+// decode + clip as in sort_decode_kernel.  Rows k .. k_cap-1 (N < pre_nms) are zero-filled.
+__global__ void __launch_bounds__(256) rank_scatter_kernel(DecodeArgs a, const uint32_t* __restrict__ sel,
+                                                           const uint64_t* __restrict__ cand_all,
+                                                           const uint32_t* __restrict__ rank_all,
+                                                           float* __restrict__ sorted_boxes,
+                                                           float* __restrict__ sorted_scores,
+                                                           int32_t* __restrict__ sorted_index,
+                                                           int32_t* __restrict__ n_sorted, int k_cap, int decode) {
+  const int f = blockIdx.y;
+  const int m = (int)sel[f * 4 + 1];
+  if (m > kMaxSortElems) return;
+  const int k = min((int)sel[f * 4 + 2], m);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) n_sorted[f] = k;
+  float* ob = sorted_boxes + (size_t)f * k_cap * 4;
+  float* os = sorted_scores + (size_t)f * k_cap;
+  int32_t* oi = sorted_index + (size_t)f * k_cap;
+  if (i >= k && i < k_cap) {          // tail rows of a frame with fewer than k_cap candidates
+    ob[i * 4 + 0] = ob[i * 4 + 1] = ob[i * 4 + 2] = ob[i * 4 + 3] = 0.f;
+    os[i] = 0.f;
+    oi[i] = 0;
+  }
+  if (i >= m) return;
+  const int r = (int)rank_all[(size_t)f * kMaxSortElems + i];
+  if (r >= k) return;
+  const int idx = (int)composite_index(cand_all[(size_t)f * a.N + i]);
+  float box[4] = {0.f, 0.f, 0.f, 0.f};
+  if (decode) {
+    const float* anc = a.anchors + (size_t)idx * 4;
+    const float* d = a.bbox_pred + ((size_t)f * a.N + idx) * 4;
+    const float an[4] = {__ldg(anc), __ldg(anc + 1), __ldg(anc + 2), __ldg(anc + 3)};
+    const float dd[4] = {__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3)};
+    decode_clip(an, dd, a.info + f * 7, box);
+  }
+  ob[r * 4 + 0] = box[0];
+  ob[r * 4 + 1] = box[1];
+  ob[r * 4 + 2] = box[2];
+  ob[r * 4 + 3] = box[3];
+  os[r] = fg_score(a.cls_prob, f, a.n_loc, a.A, idx);
+  oi[r] = idx;
 }
 
 // keep positions -> output rows (proposal_layer.py:48-55); pads the tail with zeros.
@@ -448,8 +542,24 @@ static int select_sort(int F, int n_loc, int A, const float* cls_prob, const flo
   const size_t smem = sizeof(uint64_t) * kMaxSortElems;
   B2D_CUDA(cudaFuncSetAttribute(sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DecodeArgs a{cls_prob, bbox_pred, info, anchors, n_loc, A, N};
+  const bool few = F <= kRankMaxFrames;
+  if (few) {
+    // the candidate count is only known on the device: size the grid for the largest list the path takes
+    // (CTAs beyond the count leave at once); a frame with more candidates (massive score ties) is left to the
+    // radix-select slow path of sort_decode_kernel below
+    const int cap = min(N, kMaxSortElems);
+    B2D_CUDA(cudaMemsetAsync(w.rank, 0, sizeof(uint32_t) * (size_t)F * kMaxSortElems, st));
+    dim3 rgrid(ceil_div(cap, kRankTileI), ceil_div(cap, kRankTileJ), F);
+    rank_count_kernel<<<rgrid, kRankThreads, 0, st>>>(w.sel, w.cand, N, w.rank);
+    B2D_LAUNCHED();
+    dim3 sgrid(ceil_div(max(cap, k), 256), F);
+    rank_scatter_kernel<<<sgrid, 256, 0, st>>>(a, w.sel, w.cand, w.rank, w.sorted_boxes, w.sorted_scores, w.sorted_index,
+                                               w.n_sorted, k, decode);
+    B2D_LAUNCHED();
+    if (N <= kMaxSortElems) return B2D_OK;             // the candidate list can never overflow
+  }
   sort_decode_kernel<<<F, 1024, smem, st>>>(a, w.sel, w.cand, w.sorted_boxes, w.sorted_scores, w.sorted_index,
-                                            w.n_sorted, k, decode);
+                                            w.n_sorted, k, decode, few ? 1 : 0);
   B2D_LAUNCHED();
   return B2D_OK;
 }
@@ -484,7 +594,7 @@ extern "C" int b2d_proposal(int F, int n_loc, int A, const float* cls_prob, cons
   cudaStream_t st = as_stream(stream);
   int rc = select_sort(F, n_loc, A, cls_prob, bbox_pred, info, anchors, k, 1, w, st);
   if (rc != B2D_OK) return rc;
-  rc = launch_nms_sorted(F, k, w.sorted_boxes, w.n_sorted, nms_thresh, mo, w.keep, w.num_keep, st);
+  rc = launch_nms_sorted(F, k, w.sorted_boxes, w.n_sorted, nms_thresh, mo, w.keep, w.num_keep, w.nms_kept, st);
   if (rc != B2D_OK) return rc;
   dim3 grid(ceil_div(mo, 256), F);
   proposal_gather_kernel<<<grid, 256, 0, st>>>(w.sorted_boxes, w.sorted_scores, w.sorted_index, w.keep, w.num_keep,

@@ -148,8 +148,11 @@ static Plan make_plan(int H, int W, bool allow_tma) {
 }
 
 struct Ws {
-  float4* records;        // [F][items_cap][kRecVec], grouped by part, sorted by first row within a part
+  float4* records;        // [F][items_cap][kRecVec]: item q of list entry i at slot i * 7 + q (unsorted)
   int32_t* part_start;    // [F][kMaxSplit + 1]
+  uint32_t* keys;         // [F][items_cap]: part * nb + bucket of the slot's item, ~0 for an unused slot
+  int32_t* order;         // [F][items_cap]: slots grouped by part, sorted by first row within a part
+  int32_t* ticket;        // [F]: prep CTAs of the frame that have finished (the last one sorts)
   float scale;
   int aligned;
   size_t bytes;
@@ -166,53 +169,40 @@ static Ws carve(void* base, int F, int per_frame) {
   };
   w.records = reinterpret_cast<float4*>(take((size_t)F * per_frame * kP * kRecBytes));
   w.part_start = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * (kMaxSplit + 1)));
+  w.keys = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)F * per_frame * kP));
+  w.order = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F * per_frame * kP));
+  w.ticket = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)F));
   w.bytes = off;
   return w;
 }
 
 // ------------------------------------------------------------------------------------------
-// Items of one RoI.  Calls emit(ph0, nph, first_row, last_row, slow) for each item, in ph order; the items
-// cover the 7 bin-rows exactly once.
+// Items of one RoI.  rf[ph] / rl[ph]: first / last feature row the samples of bin-row ph touch (rf > rl: none),
+// all_ok: every sample row is valid.  Calls emit(ph0, nph, first_row, last_row, slow) for each item, in ph order;
+// the items cover the 7 bin-rows exactly once.
 // A RoI whose sample rows all fit in `span_whole` rows stays ONE item (it leaves through the bulk-store tile,
 // which is worth a tighter window); otherwise it is cut into items of at most span_max rows.
-template <int S, class Emit>
-__device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_max, int span_whole, Emit emit) {
-  if (span_whole > span_max) {
-    int wf = H, wl = -1;
-    for (int ph = 0; ph < kP; ph += kP - 1)
-      for (int iy = 0; iy < S; ++iy) {
-        const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
-        if (t.ok) {
-          wf = min(wf, t.lo);
-          wl = max(wl, t.hi);
-        }
-      }
+template <class Emit>
+__device__ __forceinline__ void for_each_item(const int (&rf)[kP], const int (&rl)[kP], bool all_ok, int H, int span_max,
+                                              int span_whole, Emit emit) {
+  if (span_whole > span_max && all_ok) {
     // (rows are monotone in ph: the first and the last bin-row bound the RoI; a RoI with invalid outer
     // samples is left to the general walk below)
-    bool all_ok = true;
-    for (int ph = 0; ph < kP; ++ph)
-      for (int iy = 0; iy < S; ++iy) all_ok &= axis_tap(g.start_h, g.bin_h, ph, iy, S, H).ok;
-    if (all_ok && wl - wf + 1 > span_max && wl - wf + 1 <= span_whole) {
+    const int wf = min(rf[0], rf[kP - 1]), wl = max(rl[0], rl[kP - 1]);
+    if (wl - wf + 1 > span_max && wl - wf + 1 <= span_whole) {
       emit(0, kP, wf, wl, false);
       return;
     }
   }
   int a = 0, cf = H, cl = -1;
+#pragma unroll
   for (int ph = 0; ph < kP; ++ph) {
-    int rf = H, rl = -1;
-    for (int iy = 0; iy < S; ++iy) {
-      const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
-      if (t.ok) {
-        rf = min(rf, t.lo);
-        rl = max(rl, t.hi);
-      }
-    }
-    const int nf = min(cf, rf), nl = max(cl, rl);
+    const int nf = min(cf, rf[ph]), nl = max(cl, rl[ph]);
     if (ph > a && nl >= 0 && nl - nf + 1 > span_max) {
       emit(a, ph - a, cf, cl, false);
       a = ph;
-      cf = rf;
-      cl = rl;
+      cf = rf[ph];
+      cl = rl[ph];
     } else {
       cf = nf;
       cl = nl;
@@ -235,37 +225,170 @@ __device__ __forceinline__ void for_each_item(const RoiGeom& g, int H, int span_
 //             as aligned register pairs, then bin 6;  S == 1: {offset, hx, lx} triples
 //   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 2);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
+// One thread per list entry, kPrepThreads entries per CTA, any number of CTAs per frame: the records are written
+// unsorted (slot = entry * 7 + item), each with its sort key; the LAST CTA of a frame to finish (ticket) counting-
+// sorts the frame's slots by (part, first row) into `order`.  (One CTA per frame took 70 us at one frame per call
+// and 250 us for 2000 RoIs: a single SM, serial per RoI.)
+constexpr int kPrepThreads = 64;
+
 template <int S>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kPrepThreads)
 prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int span_whole, int nsteps,
-            int row_bytes, int items_cap, int split, Ws ws) {
-  extern __shared__ int s_buckets[];   // [split * nb] counts, offsets, fill
+            int row_bytes, int per_frame, int split, Ws ws) {
+  extern __shared__ int s_buckets[];   // last CTA of the frame: [split * nb] counts, offsets, fill
+  __shared__ int s_last;
   const int nb = nsteps + 1;
   const int nkey = split * nb;
-  int* cnt = s_buckets;
-  int* offs = s_buckets + nkey;
-  int* fill = s_buckets + 2 * nkey;
-  const int f = blockIdx.x;
-  for (int i = threadIdx.x; i < 3 * nkey; i += blockDim.x) s_buckets[i] = 0;
-  __syncthreads();
+  const int f = blockIdx.y;
+  const int items_cap = per_frame * kP;
   int first = 0, n_ent = L.n;
   if (L.seg_count) {
     first = f * L.seg_stride;
     n_ent = L.seg_count[f];
   }
-  // pass A: (part, bucket) histogram
-  for (int i = threadIdx.x; i < n_ent; i += blockDim.x) {
-    const int e = first + i;
-    const int r = L.ids ? L.ids[e] : e;
-    const float* roi = L.rois + (size_t)r * 5;
-    if (!L.seg_count && (int)roi[0] != f) continue;
-    const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
-    const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
-    const int part = i % split;
-    for_each_item<S>(g, H, span_max, span_whole, [&](int, int, int cf, int cl, bool slow) {
-      const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
-      atomicAdd(&cnt[part * nb + b], 1);
-    });
+  float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
+  uint32_t* keys = ws.keys + (size_t)f * items_cap;
+  const int i = blockIdx.x * kPrepThreads + threadIdx.x;      // list entry of this thread
+  if (i < per_frame) {
+    int n_emitted = 0;
+    bool mine = i < n_ent;
+    int r = 0;
+    float rr[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (mine) {
+      const int e = first + i;
+      r = L.ids ? L.ids[e] : e;
+      const float* roi = L.rois + (size_t)r * 5;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) rr[c] = roi[c];
+      if (!L.seg_count && (int)rr[0] != f) mine = false;
+    }
+    if (mine) {
+      const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
+      const float inv_cnt = 1.0f / g.count;
+      const int part = i % split;
+      // row range of every bin-row, once
+      int rf[kP], rl[kP];
+      bool all_ok = true;
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) {
+        rf[ph] = H;
+        rl[ph] = -1;
+#pragma unroll
+        for (int iy = 0; iy < S; ++iy) {
+          const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
+          all_ok &= t.ok;
+          if (t.ok) {
+            rf[ph] = min(rf[ph], t.lo);
+            rl[ph] = max(rl[ph], t.hi);
+          }
+        }
+      }
+      // column taps (the same for every item of the RoI).  Invalid samples carry zero weights and point at
+      // column 0 (always resident); at the clamped right border lx is 0 and the hi tap reads whatever follows
+      // the row (finite).
+      float xw[4 * kXVec];
+      {
+        int xo[2 * kP];
+        float hx[2 * kP], lx[2 * kP];
+#pragma unroll
+        for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
+          xo[k] = 0;
+          hx[k] = lx[k] = 0.0f;
+          if (k < kP * S) {
+            const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
+            if (t.ok) {
+              xo[k] = t.lo * 4;
+              hx[k] = t.wlo;
+              lx[k] = t.whi;
+            }
+          }
+        }
+        if (S == 2) {
+#pragma unroll
+          for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
+          xw[14] = xw[15] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float* q = xw + 16 + 8 * j;
+            q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
+            q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
+            q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
+            q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
+          }
+          xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2 * kP; ++k) {
+            xw[3 * k] = __int_as_float(xo[k]);
+            xw[3 * k + 1] = hx[k];
+            xw[3 * k + 2] = lx[k];
+          }
+          xw[42] = xw[43] = 0.0f;
+        }
+      }
+      for_each_item(rf, rl, all_ok, H, span_max, span_whole, [&](int ph0, int nph, int cf, int cl, bool slow) {
+        const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
+        const int sl = i * kP + n_emitted++;
+        float4* rec = recs + (size_t)sl * kRecVec;
+#pragma unroll
+        for (int v = 0; v < kXVec; ++v) rec[1 + v] = make_float4(xw[4 * v], xw[4 * v + 1], xw[4 * v + 2], xw[4 * v + 3]);
+        // distinct feature rows of the item and their weights per bin-row.  The rows are the integers of
+        // [cf, cl] that a sample touches: row y sits at position #(touched rows below y).
+        int nrows = 0;
+        if (!slow && cl >= 0) {
+          unsigned touched = 0u;
+          for (int p = 0; p < nph; ++p)
+            for (int iy = 0; iy < S; ++iy) {
+              const AxisTap t = axis_tap(g.start_h, g.bin_h, ph0 + p, iy, S, H);
+              if (t.ok) touched |= (1u << (t.lo - cf)) | (1u << (t.hi - cf));
+            }
+          nrows = __popc(touched);
+          const int rv = nph > 2 ? 2 : 1;              // matches the NPH variant the item runs on (2, 4 or 7)
+          for (unsigned rest = touched; rest; rest &= rest - 1) {
+            const int dy = __ffs(rest) - 1, y = cf + dy;
+            const int j = __popc(touched & ((1u << dy) - 1u));
+            float wy[kP];
+#pragma unroll
+            for (int q = 0; q < kP; ++q) wy[q] = 0.0f;
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+              if (p < nph) {
+                for (int iy = 0; iy < S; ++iy) {
+                  const AxisTap t = axis_tap(g.start_h, g.bin_h, ph0 + p, iy, S, H);
+                  if (!t.ok) continue;
+                  if (t.lo == y) wy[p] += t.wlo * inv_cnt;
+                  if (t.hi == y && t.hi != t.lo) wy[p] += t.whi * inv_cnt;     // clamped bottom border: hi weight is 0
+                }
+              }
+            }
+            const int off = (y % Rr) * row_bytes;
+            rec[kRowVec0 + j * rv] = make_float4(__int_as_float(off), wy[0], wy[1], wy[2]);
+            if (rv == 2) rec[kRowVec0 + j * rv + 1] = make_float4(wy[3], wy[4], wy[5], wy[6]);
+          }
+        }
+        const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
+        const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
+        rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks), 0.0f);
+        keys[sl] = (uint32_t)(part * nb + b);
+      });
+    }
+    for (int q = n_emitted; q < kP; ++q) keys[i * kP + q] = 0xFFFFFFFFu;
+  }
+  // ---- the last CTA of the frame sorts the slots
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ws.ticket + f, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  int* cnt = s_buckets;
+  int* offs = s_buckets + nkey;
+  int* fill = s_buckets + 2 * nkey;
+  for (int k = threadIdx.x; k < 3 * nkey; k += kPrepThreads) s_buckets[k] = 0;
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < items_cap; sl += kPrepThreads) {
+    const uint32_t key = __ldcg(keys + sl);
+    if (key != 0xFFFFFFFFu) atomicAdd(&cnt[key], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -279,95 +402,10 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
     for (int p = split; p <= kMaxSplit; ++p) ps[p] = run;
   }
   __syncthreads();
-  // pass B: records
-  float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
-  for (int i = threadIdx.x; i < n_ent; i += blockDim.x) {
-    const int e = first + i;
-    const int r = L.ids ? L.ids[e] : e;
-    const float* roi = L.rois + (size_t)r * 5;
-    if (!L.seg_count && (int)roi[0] != f) continue;
-    const float rr[5] = {roi[0], roi[1], roi[2], roi[3], roi[4]};
-    const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
-    const float inv_cnt = 1.0f / g.count;
-    const int part = i % split;
-    // column taps (the same for every item of the RoI).  Invalid samples carry zero weights and point at
-    // column 0 (always resident); at the clamped right border lx is 0 and the hi tap reads whatever follows
-    // the row (finite).
-    float xw[4 * kXVec];
-    {
-      int xo[2 * kP];
-      float hx[2 * kP], lx[2 * kP];
-      for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
-        xo[k] = 0;
-        hx[k] = lx[k] = 0.0f;
-        if (k < kP * S) {
-          const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
-          if (t.ok) {
-            xo[k] = t.lo * 4;
-            hx[k] = t.wlo;
-            lx[k] = t.whi;
-          }
-        }
-      }
-      if (S == 2) {
-        for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
-        xw[14] = xw[15] = 0.0f;
-        for (int j = 0; j < 3; ++j) {
-          float* q = xw + 16 + 8 * j;
-          q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
-          q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
-          q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
-          q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
-        }
-        xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
-      } else {
-        for (int k = 0; k < 2 * kP; ++k) {
-          xw[3 * k] = __int_as_float(xo[k]);
-          xw[3 * k + 1] = hx[k];
-          xw[3 * k + 2] = lx[k];
-        }
-        xw[42] = xw[43] = 0.0f;
-      }
-    }
-    for_each_item<S>(g, H, span_max, span_whole, [&](int ph0, int nph, int cf, int cl, bool slow) {
-      const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
-      float4* rec = recs + (size_t)(offs[part * nb + b] + atomicAdd(&fill[part * nb + b], 1)) * kRecVec;
-      for (int v = 0; v < kXVec; ++v) rec[1 + v] = make_float4(xw[4 * v], xw[4 * v + 1], xw[4 * v + 2], xw[4 * v + 3]);
-      // distinct feature rows of the item and their weights per bin-row
-      int nrows = 0;
-      if (!slow) {
-        int row_id[kMaxRows];
-        float wy[kMaxRows][kP];
-        for (int p = 0; p < nph; ++p) {
-          for (int iy = 0; iy < S; ++iy) {
-            const AxisTap t = axis_tap(g.start_h, g.bin_h, ph0 + p, iy, S, H);
-            if (!t.ok) continue;
-            for (int h = 0; h < 2; ++h) {
-              const int y = h ? t.hi : t.lo;
-              const float w = (h ? t.whi : t.wlo) * inv_cnt;
-              if (h && t.hi == t.lo) continue;           // clamped bottom border: hi weight is 0
-              int j = nrows - 1;
-              while (j >= 0 && row_id[j] != y) --j;      // samples are monotone: found near the end
-              if (j < 0) {
-                j = nrows++;
-                row_id[j] = y;
-                for (int q = 0; q < kP; ++q) wy[j][q] = 0.0f;
-              }
-              wy[j][p] += w;
-            }
-          }
-        }
-        const int rv = nph > 2 ? 2 : 1;              // matches the NPH variant the item runs on (2, 4 or 7)
-        for (int j = 0; j < nrows; ++j) {
-          const int off = (row_id[j] % Rr) * row_bytes;
-          rec[kRowVec0 + j * rv] = make_float4(__int_as_float(off), wy[j][0], wy[j][1], wy[j][2]);
-          if (rv == 2) rec[kRowVec0 + j * rv + 1] = make_float4(wy[j][3], wy[j][4], wy[j][5], wy[j][6]);
-        }
-      }
-      const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
-      const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
-      rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks), 0.0f);
-    });
+  int32_t* order = ws.order + (size_t)f * items_cap;
+  for (int sl = threadIdx.x; sl < items_cap; sl += kPrepThreads) {
+    const uint32_t key = __ldcg(keys + sl);
+    if (key != 0xFFFFFFFFu) order[offs[key] + atomicAdd(&fill[key], 1)] = sl;
   }
 }
 
@@ -776,6 +814,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const bool tile_out = FILL && nch == kCh && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out_g) & 15u) == 0;
   int held = -1;        // pool tile a bulk store of this warp may still be reading
   const float4* recs = records_g + (size_t)f * a.items_cap * kRecVec;
+  const int32_t* order = a.ws.order + (size_t)f * a.items_cap;
   const int item0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part]);
   const int n_items = (int)__reduce_max_sync(0xffffffffu, (unsigned)a.ws.part_start[(size_t)f * (kMaxSplit + 1) + part + 1]);
 
@@ -867,19 +906,26 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     }
   };
   pump();
+  // Items are claimed TWO ahead: the slot of a claimed item comes from the frame's sorted `order` list (one load),
+  // its record from that slot (a second, dependent load); each load has a whole item to land.
+  // (loads are unconditional - clamped index - so that a prefetch is not followed by a select that would wait
+  // for it)
+  const int last_item = max(n_items - 1, 0);
   int pending = claim();
-  float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
-  // (record loads are unconditional - clamped index - so that the prefetch is not followed by a
-  // select that would wait for it)
-  rec_next = __ldg(recs + (size_t)min(pending, max(n_items - 1, 0)) * kRecVec + lane);
+  int nxt = claim();
+  // (a frame without items leaves `order` unwritten: slots are clamped into the record array)
+  const unsigned last_slot = (unsigned)max(a.items_cap - 1, 0);
+  float4 rec_next = __ldg(recs + (size_t)min((unsigned)__ldg(order + min(pending, last_item)), last_slot) * kRecVec + lane);
+  int slot_next = (int)min((unsigned)__ldg(order + min(nxt, last_item)), last_slot);
 
   while (pending < n_items) {
     pump();
     between_items();
     slot[lane] = rec_next;
     __syncwarp();
-    const int nxt = claim();
-    rec_next = __ldg(recs + (size_t)min(nxt, n_items - 1) * kRecVec + lane);
+    rec_next = __ldg(recs + (size_t)slot_next * kRecVec + lane);
+    const int nxt2 = claim();
+    slot_next = (int)min((unsigned)__ldg(order + min(nxt2, last_item)), last_slot);
     const float4 hdr = slot[0];
     // header fields are warp-uniform; the reductions make that visible to ptxas (uniform branches / loops)
     const int r = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.x));
@@ -924,6 +970,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     }
     __syncwarp();
     pending = nxt;
+    nxt = nxt2;
   }
   // out of items: release every remaining bucket so the fill can finish
   release(nsteps);
@@ -983,6 +1030,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   ws.scale = scale;
   ws.aligned = aligned;
   const int items_cap = per_frame * kP;
+  B2D_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(int32_t) * (size_t)F, st));
   if (L.seg_count) {
     dim3 zg(L.seg_stride, F);
     zero_pad_kernel<<<zg, 256, 0, st>>>(L, C * PH * PW, out);
@@ -996,8 +1044,8 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<F, per_frame > 256 ? 512 : 256, sizeof(int) * 3 * split * nb, st>>>(                        \
-        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, items_cap, split, ws); \
+    prep_kernel<SS><<<dim3(ceil_div(per_frame, kPrepThreads), F), kPrepThreads, sizeof(int) * 3 * split * nb, st>>>( \
+        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, per_frame, split, ws); \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
     fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap, feat, ws.records, L.rois, out);                    \

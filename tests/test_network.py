@@ -136,6 +136,7 @@ def test_train_step_targets_match_the_oracle(net_type):
     net, cfg = make_net(net_type)
     ptl.RNG_DEVICE = "cpu"
     net._rng_device = torch.device("cpu")
+    cfg.TRAIN.USE_GT = True          # GT boxes join the RoIs (proposal_target_layer.py:35-41): guarantees foreground samples
     try:
         data, info, gt, true_gt = frame(net_type, 1)
         opt = torch.optim.SGD(net.parameters(), lr=1e-3)
@@ -147,7 +148,7 @@ def test_train_step_targets_match_the_oracle(net_type):
         p, at, pt = net._predictions, net._anchor_targets, net._proposal_targets
         A, E, K = net._num_anchors, net._bbox_elem, 3
         Hf, Wf = p["rpn_cls_prob"].shape[1:3]
-        ocfg = O.GlueCfg(net_type=net_type)
+        ocfg = O.GlueCfg(net_type=net_type, use_gt=True)
         torch.manual_seed(7)
         blob, sc, a3k = O.proposal_layer(p["rpn_cls_prob"].detach().cpu(), p["rpn_bbox_pred"].detach().cpu(), info, "TRAIN",
                                          net._anchors.cpu(), net._anchors_3d.cpu(), A, cfg=ocfg, stable_sort=True)
@@ -165,4 +166,4 @@ def test_train_step_targets_match_the_oracle(net_type):
         assert rois.shape[1] == 5 and cls_prob.shape == (rois.shape[0], K) and bbox_pred.shape == (rois.shape[0], K * E)
     finally:
         ptl.RNG_DEVICE = None
-        cfg.NET_TYPE = "lidar"
+        cfg.NET_TYPE, cfg.TRAIN.USE_GT = "lidar", False
