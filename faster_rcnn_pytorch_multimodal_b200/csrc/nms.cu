@@ -20,7 +20,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kTile = 64;
 constexpr int kGroup = kNmsThreads / kTile;  // threads cooperating on one candidate (16)
 constexpr int kKeptSmem = 2560;              // kept boxes cached in shared memory (40 KB)
-constexpr int kNmsClusterMaxFrames = 16;     // up to this many frames per call take the cluster kernel
+constexpr int kNmsClusterMaxFrames = 8;      // up to this many frames per call take the cluster kernel (one GPC each)
 
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float area_a, const float4 b, const float thr_f) {
   const float w = fmaxf(0.0f, fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
@@ -124,24 +124,25 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sorted_kernel(const float4* _
 
 
 // ------------------------------------------------------------------------------------------
-// Few-frame path: one thread-block CLUSTER (8 CTAs x 1024 threads) per frame instead of one CTA.
+// Few-frame path: one thread-block CLUSTER (16 CTAs x 1024 threads) per frame instead of one CTA.
 // The single-CTA kernel above is bound by one SM's issue rate (12 M IoUs for a 12000 -> 2000 train frame) and by
 // its serial per-tile resolve; with one frame per call - what the reference API issues - 147 SMs idle meanwhile.
-// Candidates are taken in chunks of 1024.  Per chunk:
-//   A (all 8 CTAs, 128 candidates each): every candidate against the kept list so far (global memory, written by
-//     the sweeper) -> dead bits; and its row of the chunk's 1024 x 1024 suppression bitmask (16 words of 64 bits,
-//     columns above the diagonal only).  Rows and dead bits are written straight into CTA 0's shared memory
-//     through DSMEM (st.shared::cluster).
+// Candidates are taken in chunks of 512.  Per chunk:
+//   A (all 16 CTAs, 32 candidates each, ONE WARP per candidate): the candidate against the kept list so far
+//     (global memory, written by the sweeper; lanes stride over it) -> dead bit; and its row of the chunk's
+//     512 x 512 suppression bitmask (8 words of 64 bits, columns above the diagonal only): lane l evaluates
+//     columns l, l + 32, ... and two ballots assemble each word.  Rows and dead flags are written straight into
+//     CTA 0's shared memory through DSMEM (st.shared::cluster).
 //   cluster barrier
-//   B (one warp of CTA 0): greedy sweep.  Lane w < 16 holds the "removed" word of column tile w in a register; for
+//   B (one warp of CTA 0): greedy sweep.  Lane w < 8 holds the "removed" word of column tile w in a register; for
 //     every surviving candidate the warp ORs its bitmask row in (one 8-byte load per lane) and resolves the next
 //     survivor of the tile with a find-first-set - ~45 cycles per kept box, no __syncthreads, no global bitmask.
 //   CTA 0 appends the kept boxes to the global kept list and publishes (count, done); cluster barrier.
 // Same decisions as the single-CTA kernel: both evaluate iou_exceeds() on the same operands.
-constexpr int kClusterCtas = 8;
-constexpr int kChunk = 1024;                         // candidates per chunk
-constexpr int kChunkWords = kChunk / 64;             // 16
-constexpr int kRowsPerCta = kChunk / kClusterCtas;   // 128
+constexpr int kClusterCtas = 16;                     // non-portable cluster size (B200 allows 16 with the opt-in)
+constexpr int kChunk = 512;                          // candidates per chunk
+constexpr int kChunkWords = kChunk / 64;             // 8
+constexpr int kRowsPerCta = kChunk / kClusterCtas;   // 32 = warps per CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -161,9 +162,11 @@ __device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long
 }
 
 struct NmsClusterSmem {
-  unsigned long long mask[kChunk][kChunkWords];   // CTA 0: suppression rows of the chunk (128 KB)
+  unsigned long long mask[kChunk][kChunkWords];   // CTA 0: suppression rows of the chunk (32 KB)
+  float4 kept[kKeptSmem];                          // every CTA: its copy of the kept list (the rest stays in L2)
   float4 box[kChunk];                              // the chunk's boxes (every CTA loads them)
-  unsigned long long dead[kChunkWords];            // CTA 0: candidates suppressed by earlier chunks' kept boxes
+  int dead[kChunk];                                // CTA 0: candidate is suppressed by an earlier chunk's kept box
+  int newk[kChunk];                                // CTA 0: chunk rows kept by this sweep
   int state[2];                                    // {kept count, done}: written by CTA 0 into every CTA
 };
 
@@ -171,73 +174,72 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* __restrict__ n_valid, float thr_f,
                    int max_keep, int32_t* __restrict__ keep_all, int32_t* __restrict__ num_keep,
                    float4* __restrict__ kept_boxes_all) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsClusterSmem& S = *reinterpret_cast<NmsClusterSmem*>(smem_raw);
+  extern __shared__ __align__(16) unsigned char nms_smem_raw[];
+  NmsClusterSmem& S = *reinterpret_cast<NmsClusterSmem*>(nms_smem_raw);
   const int f = blockIdx.y;
   const uint32_t cta = cluster_ctarank();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* boxes = boxes_all + (size_t)f * n;
   int32_t* keep = keep_all + (size_t)f * max_keep;
   float4* kept_boxes = kept_boxes_all + (size_t)f * max_keep;
   const int nv = n_valid ? min(n_valid[f], n) : n;
   if (tid < 2) S.state[tid] = 0;
-  if (tid < kChunkWords) S.dead[tid] = 0ull;
   cluster_sync_all();
   const uint32_t mask0 = map_to_cta(smem_u32(&S.mask[0][0]), 0);
   const uint32_t dead0 = map_to_cta(smem_u32(&S.dead[0]), 0);
 
+  int K_cached = 0;                                   // kept boxes already copied into S.kept
   for (int base = 0; base < nv; base += kChunk) {
     const int K = S.state[0];
     const int cn = min(kChunk, nv - base);            // candidates in this chunk
-    S.box[tid] = tid < cn ? boxes[base + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < kChunk) S.box[tid] = tid < cn ? boxes[base + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // the boxes the last sweep kept: one coalesced L2 read instead of a dependent load per 32 comparisons
+    for (int q = K_cached + tid; q < min(K, kKeptSmem); q += kNmsThreads) S.kept[q] = __ldcg(kept_boxes + q);
+    K_cached = K;
     __syncthreads();
-    // ---- A: this CTA's 128 candidates, 8 threads each
-    const int row = (int)cta * kRowsPerCta + (tid >> 3);   // candidate within the chunk
-    const int sub = tid & 7;
-    const float4 me = S.box[row];
-    const float my_area = fmul(fsub(me.z, me.x), fsub(me.w, me.y));
-    bool dead = false;
-    unsigned long long w0 = 0ull, w1 = 0ull;
+    // ---- A: this CTA's 32 candidates, one warp each
+    const int row = (int)cta * kRowsPerCta + warp;   // candidate within the chunk
     if (row < cn) {
-      for (int kk = sub; kk < K; kk += 8) {
-        if (iou_exceeds(me, my_area, __ldcg(kept_boxes + kk), thr_f)) {
+      const float4 me = S.box[row];
+      const float my_area = fmul(fsub(me.z, me.x), fsub(me.w, me.y));
+      bool dead = false;
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        const bool hit = kk < K && iou_exceeds(me, my_area, kk < kKeptSmem ? S.kept[kk] : __ldcg(kept_boxes + kk), thr_f);
+        if (__any_sync(0xFFFFFFFFu, hit)) {
           dead = true;
           break;
         }
       }
-      // columns [sub*128, sub*128 + 128) of this row, above the diagonal
-      const int c0 = sub * 128;
-      if (c0 + 127 > row) {
-#pragma unroll 4
-        for (int c = 0; c < 128; ++c) {
-          const int j = c0 + c;
-          if (j > row && j < cn && iou_exceeds(me, my_area, S.box[j], thr_f)) {
-            if (c < 64) w0 |= 1ull << c; else w1 |= 1ull << (c - 64);
-          }
-        }
-      }
-    }
-    // row -> CTA 0 (two words per thread); dead bit of the candidate -> CTA 0
-    st_cluster_u64(mask0 + (uint32_t)(row * kChunkWords + sub * 2) * 8u, w0);
-    st_cluster_u64(mask0 + (uint32_t)(row * kChunkWords + sub * 2 + 1) * 8u, w1);
-    const unsigned db = __ballot_sync(0xFFFFFFFFu, dead);     // 4 candidates per warp, 8 lanes each
-    if ((tid & 31) == 0) {
-      unsigned long long bits = 0ull;
-      const int r0 = (int)cta * kRowsPerCta + (tid >> 3);     // first candidate of this warp
+      if (lane == 0) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(dead0 + (uint32_t)row * 4u), "r"(dead ? 1 : 0) : "memory");
+      if (!dead) {
+        // (a dead candidate's row is never read by the sweep)
+        unsigned long long mine = 0ull;              // lane w < 8 ends up with word w
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if ((db >> (8 * q)) & 0xFFu) bits |= 1ull << ((r0 + q) & 63);
-      // 16 warps of one CTA cover two 64-bit words: accumulate with a remote atomic
-      if (bits) {
-        const uint32_t a = dead0 + (uint32_t)(r0 >> 6) * 8u;
-        asm volatile("red.shared::cluster.or.b64 [%0], %1;" ::"r"(a), "l"(bits) : "memory");
+        for (int w = 0; w < kChunkWords; ++w) {
+          unsigned lo = 0u, hi = 0u;
+          if (64 * w + 63 > row) {                   // warp-uniform: the word has columns above the diagonal
+            const int j0 = 64 * w + lane, j1 = j0 + 32;
+            lo = __ballot_sync(0xFFFFFFFFu, j0 > row && j0 < cn && iou_exceeds(me, my_area, S.box[j0], thr_f));
+            hi = __ballot_sync(0xFFFFFFFFu, j1 > row && j1 < cn && iou_exceeds(me, my_area, S.box[j1], thr_f));
+          }
+          if (lane == w) mine = ((unsigned long long)hi << 32) | lo;
+        }
+        if (lane < kChunkWords) st_cluster_u64(mask0 + (uint32_t)(row * kChunkWords + lane) * 8u, mine);
       }
     }
     cluster_sync_all();
     // ---- B: sweep (first warp of CTA 0)
-    if (cta == 0 && tid < 32) {
-      const int lane = tid;
-      unsigned long long rem = lane < kChunkWords ? S.dead[lane] : 0ull;
+    if (cta == 0 && warp == 0) {
+      // lane w < 8: "removed" word of column tile w, seeded with the candidates the kept list already suppresses
+      unsigned long long rem = 0ull;
+#pragma unroll
+      for (int w = 0; w < kChunkWords; ++w) {
+        const int j0 = 64 * w + lane, j1 = j0 + 32;
+        const unsigned lo = __ballot_sync(0xFFFFFFFFu, j0 < cn && S.dead[j0] != 0);
+        const unsigned hi = __ballot_sync(0xFFFFFFFFu, j1 < cn && S.dead[j1] != 0);
+        if (lane == w) rem = ((unsigned long long)hi << 32) | lo;
+      }
       int k = K;
       for (int t = 0; t < kChunkWords && k < max_keep; ++t) {
         const int tile_n = min(64, cn - t * 64);
@@ -250,7 +252,10 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
           const unsigned long long diag = S.mask[r][t];                          // broadcast load
           if (lane < kChunkWords) rem |= S.mask[r][lane];
           alive &= ~(diag | (1ull << i));
-          if (lane == 0) keep[k] = base + r;
+          if (lane == 0) {
+            keep[k] = base + r;
+            S.newk[k - K] = r;
+          }
           ++k;
         }
       }
@@ -259,8 +264,7 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
     if (cta == 0) {
       __syncthreads();
       const int k1 = S.state[0];
-      for (int q = K + tid; q < k1; q += kNmsThreads) kept_boxes[q] = S.box[keep[q] - base];
-      if (tid < kChunkWords) S.dead[tid] = 0ull;
+      for (int q = tid; q < k1 - K; q += kNmsThreads) kept_boxes[K + q] = S.box[S.newk[q]];
       __threadfence();
       __syncthreads();
       // publish (count, done) to every CTA of the cluster
@@ -281,6 +285,36 @@ size_t nms_cluster_workspace_bytes(int F, int max_keep) {
   return F <= kNmsClusterMaxFrames ? align_up(sizeof(float4) * (size_t)F * (max_keep > 0 ? max_keep : 0), 256) : 0;
 }
 
+// 16-CTA clusters need the non-portable opt-in and a GPC with 16 free SMs: asked once per process.
+static bool cluster_nms_available() {
+  static const bool ok = [] {
+    if (cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(NmsClusterSmem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kClusterCtas, 1);
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = sizeof(NmsClusterSmem);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, nms_cluster_kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return n > 0;
+  }();
+  return ok;
+}
+
 // kept_scratch: nms_cluster_workspace_bytes(F, max_keep) bytes or NULL (then every frame count takes the
 // single-CTA kernel).
 int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, double thresh, int max_keep,
@@ -289,13 +323,11 @@ int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, 
     B2D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t) * F, st));
     return B2D_OK;
   }
-  if (kept_scratch && F <= kNmsClusterMaxFrames && n > 2 * kTile) {
-    const size_t smem = sizeof(NmsClusterSmem);
-    B2D_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (kept_scratch && F <= kNmsClusterMaxFrames && n > 2 * kTile && cluster_nms_available()) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kClusterCtas, F);
     cfg.blockDim = dim3(kNmsThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = sizeof(NmsClusterSmem);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -317,9 +349,17 @@ int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, 
 
 }  // namespace b2d
 
+extern "C" size_t b2d_nms_workspace_bytes(int F, int max_keep) {
+  if (F <= 0 || max_keep <= 0) return 0;
+  return b2d::nms_cluster_workspace_bytes(F, max_keep);
+}
+
 extern "C" int b2d_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, double thresh, int max_keep,
-                              int32_t* keep, int32_t* num_keep, void* stream) {
+                              int32_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
   if (F <= 0 || n < 0 || !boxes || !keep || !num_keep) return B2D_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(boxes) & 15u) != 0) return B2D_ERR_INVALID_ARG;  // float4 loads
-  return b2d::launch_nms_sorted(F, n, boxes, n_valid, thresh, max_keep, keep, num_keep, nullptr, b2d::as_stream(stream));
+  // the workspace is optional: without it (or with more frames than the cluster path takes) the single-CTA kernel runs
+  const size_t need = b2d::nms_cluster_workspace_bytes(F, max_keep);
+  void* ws = (workspace && need && workspace_bytes >= need) ? workspace : nullptr;
+  return b2d::launch_nms_sorted(F, n, boxes, n_valid, thresh, max_keep, keep, num_keep, ws, b2d::as_stream(stream));
 }

@@ -17,8 +17,10 @@
 //     A 5x5-pixel RoI costs 5 rows x 28 taps = 140 wavefronts instead of 784; only RoIs whose bins
 //     are taller than two pixels still pay 16 taps per output (their samples share nothing).
 //
-// Data flow per CTA = (32-channel group, frame, part of the frame's RoIs).  The CTA streams the feature
-// rows of its 32 channels top to bottom through a ring of nblk blocks of St rows.  Lane c reads pixel
+// Data flow per CTA = (32-channel group, frame, band of rows - one band unless the call has few frames).  The CTA
+// streams the feature rows of its band, 32 channels, top to bottom through a ring of nblk blocks of St rows
+// (with few frames per call - the reference API issues ONE - the frame is cut into up to 4 bands so that 128
+// CTAs work on it and each fills a quarter of the rows).  Lane c reads pixel
 // (row, x) of channel c at word  slot*row_words + c*lane_stride + x  with an ODD lane_stride (W + 1 for
 // even W), so the 32 lanes of a tap always hit 32 different banks.
 //
@@ -90,7 +92,7 @@ constexpr int kMaxRows = 10;       // distinct feature rows per item
 constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
-constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each takes the RoIs e % split == part
+constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each streams one band of rows
 
 constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps
 constexpr int kTileWords = kCh * kP * kP;
@@ -225,22 +227,48 @@ __device__ __forceinline__ void for_each_item(const int (&rf)[kP], const int (&r
 //             as aligned register pairs, then bin 6;  S == 1: {offset, hx, lx} triples
 //   [12..]    per distinct feature row: {ring byte offset, wy[0..2]} (+ {wy[3..6]} when nph > 2);
 //             wy[p] = weight of that row in bin-row ph0 + p, already divided by the sample count
-// One thread per list entry, kPrepThreads entries per CTA, any number of CTAs per frame: the records are written
-// unsorted (slot = entry * 7 + item), each with its sort key; the LAST CTA of a frame to finish (ticket) counting-
-// sorts the frame's slots by (part, first row) into `order`.  (One CTA per frame took 70 us at one frame per call
-// and 250 us for 2000 RoIs: a single SM, serial per RoI.)
-constexpr int kPrepThreads = 64;
+// One WARP per list entry, kPrepWarps entries per CTA, any number of CTAs per frame.  The lanes of a warp hold the
+// 14 row taps (lanes 0..13) and the 14 column taps (lanes 16..29) of the RoI - one axis_tap() each - and build the
+// item records cooperatively: lane v writes float4 v of the 512-byte record, pulling what it needs from the tap
+// lanes with shuffles.  Records are written unsorted (slot = entry * 7 + item), each with its sort key; the LAST
+// CTA of a frame to finish (ticket) counting-sorts the frame's slots by (part, first row) into `order`.
+// (One CTA per frame with a thread per RoI took 70 us at one frame per call and 250 us for 2000 RoIs: a single SM
+// running ~10 000 serial instructions per RoI.)
+constexpr int kPrepWarps = 8;
+constexpr int kPrepThreads = kPrepWarps * 32;
+constexpr int kPrepKeyCache = 4096;      // slots whose sort keys the sorting CTA keeps in shared memory (16 KB)
+
+// word e of the column-tap block (11 float4 = 44 words) = field f of column tap k, packed k | f << 4
+// (f: 0 byte offset of the lo column, 1 weight of the lo column, 2 weight of the hi column, 3 zero)
+__host__ __device__ constexpr int xw_map(int S, int e) {
+  if (S == 2) {
+    if (e < 14) return e;
+    if (e < 16) return 3 << 4;
+    if (e < 40) {
+      const int j = (e - 16) / 8, m = (e - 16) % 8;
+      // wa = hx[4j], hx[4j+2]; wb = lx[4j], lx[4j+2]; wc = hx[4j+1], hx[4j+3]; wd = lx[4j+1], lx[4j+3]
+      const int k = 4 * j + (m / 4) + 2 * (m % 2);
+      const int f = ((m / 2) % 2) ? 2 : 1;
+      return k | (f << 4);
+    }
+    return (12 + (e - 40) / 2) | ((((e - 40) % 2) ? 2 : 1) << 4);
+  }
+  if (e < 42) return ((e / 3) < 7 ? e / 3 : 0) | (((e / 3) < 7 ? e % 3 : 3) << 4);
+  return 3 << 4;
+}
 
 template <int S>
 __global__ void __launch_bounds__(kPrepThreads)
 prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, int span_max, int span_whole, int nsteps,
-            int row_bytes, int per_frame, int split, Ws ws) {
+            int row_bytes, int per_frame, int split, int band_rows, Ws ws) {
   extern __shared__ int s_buckets[];   // last CTA of the frame: [split * nb] counts, offsets, fill
   __shared__ int s_last;
+  constexpr int NT = kP * S;           // taps per axis
   const int nb = nsteps + 1;
   const int nkey = split * nb;
   const int f = blockIdx.y;
   const int items_cap = per_frame * kP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int first = 0, n_ent = L.n;
   if (L.seg_count) {
     first = f * L.seg_stride;
@@ -248,7 +276,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
   }
   float4* recs = ws.records + (size_t)f * items_cap * kRecVec;
   uint32_t* keys = ws.keys + (size_t)f * items_cap;
-  const int i = blockIdx.x * kPrepThreads + threadIdx.x;      // list entry of this thread
+  const int i = blockIdx.x * kPrepWarps + warp;      // list entry of this warp
   if (i < per_frame) {
     int n_emitted = 0;
     bool mine = i < n_ent;
@@ -259,120 +287,125 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
       r = L.ids ? L.ids[e] : e;
       const float* roi = L.rois + (size_t)r * 5;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) rr[c] = roi[c];
+      for (int c = 0; c < 5; ++c) rr[c] = __ldg(roi + c);
       if (!L.seg_count && (int)rr[0] != f) mine = false;
     }
-    if (mine) {
+    if (mine) {      // (warp-uniform)
       const RoiGeom g = roi_geometry(rr, scale, kP, kP, S, aligned != 0);
       const float inv_cnt = 1.0f / g.count;
-      const int part = i % split;
-      // row range of every bin-row, once
+      // this lane's tap: lanes [0, NT) rows, lanes [16, 16 + NT) columns; the others compute a dummy
+      const bool is_x = lane >= 16;
+      const int k_mine = min(is_x ? lane - 16 : lane, NT - 1);
+      const AxisTap t = axis_tap(is_x ? g.start_w : g.start_h, is_x ? g.bin_w : g.bin_h, k_mine / S, k_mine % S, S,
+                                 is_x ? W : H);
+      const unsigned okm = __ballot_sync(0xFFFFFFFFu, t.ok);
+      // row lanes carry weights already divided by the sample count
+      const float wlo = is_x ? t.wlo : t.wlo * inv_cnt, whi = is_x ? t.whi : t.whi * inv_cnt;
+      const unsigned yok = okm & ((1u << NT) - 1u);
+      // row range of every bin-row (uniform in the warp)
       int rf[kP], rl[kP];
-      bool all_ok = true;
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph) {
         rf[ph] = H;
         rl[ph] = -1;
 #pragma unroll
         for (int iy = 0; iy < S; ++iy) {
-          const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, S, H);
-          all_ok &= t.ok;
-          if (t.ok) {
-            rf[ph] = min(rf[ph], t.lo);
-            rl[ph] = max(rl[ph], t.hi);
+          const int k = ph * S + iy;
+          const int lo_k = __shfl_sync(0xFFFFFFFFu, t.lo, k), hi_k = __shfl_sync(0xFFFFFFFFu, t.hi, k);
+          if (yok & (1u << k)) {
+            rf[ph] = min(rf[ph], lo_k);
+            rl[ph] = max(rl[ph], hi_k);
           }
         }
       }
-      // column taps (the same for every item of the RoI).  Invalid samples carry zero weights and point at
-      // column 0 (always resident); at the clamped right border lx is 0 and the hi tap reads whatever follows
-      // the row (finite).
-      float xw[4 * kXVec];
+      const bool all_ok = yok == (1u << NT) - 1u;
+      // float4 `lane` of the record, column-tap part (lanes 1..11), the same for every item of the RoI.  Invalid
+      // samples carry zero weights and point at column 0 (always resident); at the clamped right border lx is 0
+      // and the hi tap reads whatever follows the row (finite).
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
       {
-        int xo[2 * kP];
-        float hx[2 * kP], lx[2 * kP];
+        const float xoff = __int_as_float(t.ok ? t.lo * 4 : 0);
+        float c[4];
 #pragma unroll
-        for (int k = 0; k < 2 * kP; ++k) {                 // column slot: pw = k / 2, ix = k % 2 (S == 2)
-          xo[k] = 0;
-          hx[k] = lx[k] = 0.0f;
-          if (k < kP * S) {
-            const AxisTap t = axis_tap(g.start_w, g.bin_w, S == 2 ? k / 2 : k, S == 2 ? k % 2 : 0, S, W);
-            if (t.ok) {
-              xo[k] = t.lo * 4;
-              hx[k] = t.wlo;
-              lx[k] = t.whi;
-            }
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int m = xw_map(S, min(max(4 * (lane - 1) + q, 0), 4 * kXVec - 1));
+          const int src = 16 + (m & 15), fld = m >> 4;
+          const float a0 = __shfl_sync(0xFFFFFFFFu, xoff, src), a1 = __shfl_sync(0xFFFFFFFFu, t.wlo, src),
+                      a2 = __shfl_sync(0xFFFFFFFFu, t.whi, src);
+          c[q] = fld == 0 ? a0 : (fld == 1 ? a1 : (fld == 2 ? a2 : 0.0f));
         }
-        if (S == 2) {
-#pragma unroll
-          for (int k = 0; k < 2 * kP; ++k) xw[k] = __int_as_float(xo[k]);
-          xw[14] = xw[15] = 0.0f;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            float* q = xw + 16 + 8 * j;
-            q[0] = hx[4 * j], q[1] = hx[4 * j + 2];         // wa
-            q[2] = lx[4 * j], q[3] = lx[4 * j + 2];         // wb
-            q[4] = hx[4 * j + 1], q[5] = hx[4 * j + 3];     // wc
-            q[6] = lx[4 * j + 1], q[7] = lx[4 * j + 3];     // wd
-          }
-          xw[40] = hx[12], xw[41] = lx[12], xw[42] = hx[13], xw[43] = lx[13];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 2 * kP; ++k) {
-            xw[3 * k] = __int_as_float(xo[k]);
-            xw[3 * k + 1] = hx[k];
-            xw[3 * k + 2] = lx[k];
-          }
-          xw[42] = xw[43] = 0.0f;
-        }
+        xv = make_float4(c[0], c[1], c[2], c[3]);
       }
+      // the items of the RoI (at most 7), one per lane: ph0 | nph << 4 | slow << 8 | cf << 9 | cl << 20
+      // (the walk is uniform in the warp; keeping the list in lanes avoids four inlined copies of the record code)
+      int my_item = 0;
       for_each_item(rf, rl, all_ok, H, span_max, span_whole, [&](int ph0, int nph, int cf, int cl, bool slow) {
-        const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
-        const int sl = i * kP + n_emitted++;
-        float4* rec = recs + (size_t)sl * kRecVec;
-#pragma unroll
-        for (int v = 0; v < kXVec; ++v) rec[1 + v] = make_float4(xw[4 * v], xw[4 * v + 1], xw[4 * v + 2], xw[4 * v + 3]);
-        // distinct feature rows of the item and their weights per bin-row.  The rows are the integers of
-        // [cf, cl] that a sample touches: row y sits at position #(touched rows below y).
-        int nrows = 0;
-        if (!slow && cl >= 0) {
-          unsigned touched = 0u;
-          for (int p = 0; p < nph; ++p)
-            for (int iy = 0; iy < S; ++iy) {
-              const AxisTap t = axis_tap(g.start_h, g.bin_h, ph0 + p, iy, S, H);
-              if (t.ok) touched |= (1u << (t.lo - cf)) | (1u << (t.hi - cf));
-            }
-          nrows = __popc(touched);
-          const int rv = nph > 2 ? 2 : 1;              // matches the NPH variant the item runs on (2, 4 or 7)
-          for (unsigned rest = touched; rest; rest &= rest - 1) {
-            const int dy = __ffs(rest) - 1, y = cf + dy;
-            const int j = __popc(touched & ((1u << dy) - 1u));
-            float wy[kP];
-#pragma unroll
-            for (int q = 0; q < kP; ++q) wy[q] = 0.0f;
-#pragma unroll
-            for (int p = 0; p < kP; ++p) {
-              if (p < nph) {
-                for (int iy = 0; iy < S; ++iy) {
-                  const AxisTap t = axis_tap(g.start_h, g.bin_h, ph0 + p, iy, S, H);
-                  if (!t.ok) continue;
-                  if (t.lo == y) wy[p] += t.wlo * inv_cnt;
-                  if (t.hi == y && t.hi != t.lo) wy[p] += t.whi * inv_cnt;     // clamped bottom border: hi weight is 0
-                }
-              }
-            }
-            const int off = (y % Rr) * row_bytes;
-            rec[kRowVec0 + j * rv] = make_float4(__int_as_float(off), wy[0], wy[1], wy[2]);
-            if (rv == 2) rec[kRowVec0 + j * rv + 1] = make_float4(wy[3], wy[4], wy[5], wy[6]);
-          }
-        }
-        const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
-        const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
-        rec[0] = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks), 0.0f);
-        keys[sl] = (uint32_t)(part * nb + b);
+        const int packed = ph0 | (nph << 4) | ((slow ? 1 : 0) << 8) | (min(cf, 2047) << 9) | ((cl + 1) << 20);
+        if (lane == n_emitted) my_item = packed;
+        ++n_emitted;
       });
+#pragma unroll 1
+      for (int it = 0; it < n_emitted; ++it) {
+        const int packed = __shfl_sync(0xFFFFFFFFu, my_item, it);
+        const int ph0 = packed & 15, nph = (packed >> 4) & 15;
+        const bool slow = (packed >> 8) & 1;
+        const int cl = (packed >> 20) - 1;
+        const int cf = cl < 0 ? H : (packed >> 9) & 2047;
+        const int b = slow ? nsteps : (cl < 0 ? 0 : cf / St);
+        // the CTA of band `part` streams rows [part * band_rows, (part + 1) * band_rows + window): an item belongs
+        // to the band of its first row (items without a valid row go to band 0, slow items need no rows)
+        const int part = cl < 0 ? 0 : min(split - 1, cf / band_rows);
+        const int sl = i * kP + it;
+        float4* rec = recs + (size_t)sl * kRecVec;
+        // distinct feature rows of the item: the integers of [cf, cl] that one of its samples touches
+        const bool in_item = !is_x && lane >= ph0 * S && lane < (ph0 + nph) * S && t.ok;
+        unsigned touched = 0u;
+        if (!slow && cl >= 0) {
+          const unsigned mine_bits = in_item ? (1u << (t.lo - cf)) | (1u << (t.hi - cf)) : 0u;
+          touched = __reduce_or_sync(0xFFFFFFFFu, mine_bits);
+        }
+        const int nrows = __popc(touched);
+        const int rv = nph > 2 ? 2 : 1;                // matches the NPH variant the item runs on (2, 4 or 7)
+        float4 out = xv;
+        if (lane == 0) {
+          const int code = ph0 | (nph << 4) | (nrows << 8) | ((slow ? 1 : 0) << 16);
+          const int blocks = b | ((cl < 0 ? 0 : cl / St) << 16);
+          out = make_float4(__int_as_float(r), __int_as_float(code), __int_as_float(blocks), 0.0f);
+        }
+        // lanes 12..31: row entry j = (lane - 12) / rv, half (lane - 12) % rv:
+        //   half 0 {ring byte offset, wy[0..2]}, half 1 {wy[3..6]};  wy[p] = weight of the row in bin-row ph0 + p
+        const int jl = max(lane - kRowVec0, 0);
+        const int jrow = rv == 2 ? jl >> 1 : jl, half = rv == 2 ? jl & 1 : 0;
+        int y = -1;                                    // the jrow-th touched row
+#pragma unroll
+        for (int bit = 0; bit < kMaxRows; ++bit)
+          if (((touched >> bit) & 1u) && __popc(touched & ((1u << bit) - 1u)) == jrow) y = cf + bit;
+        float wv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int p = half * 3 + c - (half ? 0 : 1);          // half 0: c = 1..3 -> p = 0..2; half 1: p = 3..6
+          float w = 0.0f;
+#pragma unroll
+          for (int iy = 0; iy < S; ++iy) {
+            const int k = min(max((ph0 + p) * S + iy, 0), NT - 1);
+            const int lo_k = __shfl_sync(0xFFFFFFFFu, t.lo, k), hi_k = __shfl_sync(0xFFFFFFFFu, t.hi, k);
+            const float wl_k = __shfl_sync(0xFFFFFFFFu, wlo, k), wh_k = __shfl_sync(0xFFFFFFFFu, whi, k);
+            const bool use = p >= 0 && p < nph && (yok & (1u << k)) && y >= 0;
+            if (use && lo_k == y) w += wl_k;
+            if (use && hi_k == y && hi_k != lo_k) w += wh_k;    // clamped bottom border: hi == lo, its weight is 0
+          }
+          wv[c] = w;
+        }
+        if (lane >= kRowVec0) {
+          int off = 0;
+          if (y >= 0) off = (Rr == H ? y : y % Rr) * row_bytes;
+          out = half == 0 ? make_float4(__int_as_float(off), wv[1], wv[2], wv[3]) : make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        rec[lane] = out;
+        if (lane == 0) keys[sl] = (uint32_t)(part * nb + b);
+      }
     }
-    for (int q = n_emitted; q < kP; ++q) keys[i * kP + q] = 0xFFFFFFFFu;
+    if (lane >= n_emitted && lane < kP) keys[i * kP + lane] = 0xFFFFFFFFu;
   }
   // ---- the last CTA of the frame sorts the slots
   __threadfence();
@@ -386,25 +419,43 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
   int* fill = s_buckets + 2 * nkey;
   for (int k = threadIdx.x; k < 3 * nkey; k += kPrepThreads) s_buckets[k] = 0;
   __syncthreads();
+  // keys: global -> shared (independent loads, one L2 round trip), counted on the way
+  uint32_t* skey = reinterpret_cast<uint32_t*>(s_buckets + 3 * nkey);
+  const bool cached = items_cap <= kPrepKeyCache;
+#pragma unroll 4
   for (int sl = threadIdx.x; sl < items_cap; sl += kPrepThreads) {
     const uint32_t key = __ldcg(keys + sl);
+    if (cached) skey[sl] = key;
     if (key != 0xFFFFFFFFu) atomicAdd(&cnt[key], 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
+  if (warp == 0) {
+    // exclusive prefix over the nkey counts: each lane sums a run of keys, a warp scan joins the runs
+    const int per = (nkey + 31) / 32;
+    const int k0 = min(lane * per, nkey), k1 = min(k0 + per, nkey);
+    int sum = 0;
+    for (int k = k0; k < k1; ++k) sum += cnt[k];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int run = incl - sum;
     int32_t* ps = ws.part_start + (size_t)f * (kMaxSplit + 1);
-    for (int k = 0; k < nkey; ++k) {
+    for (int k = k0; k < k1; ++k) {
       if (k % nb == 0) ps[k / nb] = run;
       offs[k] = run;
       run += cnt[k];
     }
-    for (int p = split; p <= kMaxSplit; ++p) ps[p] = run;
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (lane >= split && lane <= kMaxSplit) ps[lane] = total;
   }
   __syncthreads();
   int32_t* order = ws.order + (size_t)f * items_cap;
+#pragma unroll 4
   for (int sl = threadIdx.x; sl < items_cap; sl += kPrepThreads) {
-    const uint32_t key = __ldcg(keys + sl);
+    const uint32_t key = cached ? skey[sl] : __ldcg(keys + sl);
     if (key != 0xFFFFFFFFu) order[offs[key] + atomicAdd(&fill[key], 1)] = sl;
   }
 }
@@ -672,7 +723,7 @@ struct KArgs {
   RoiList L;
   int C, H, W;
   int lane_stride, row_words, stage_w;
-  int St, nblk, nbk, nsteps, items_cap;
+  int St, nblk, nbk, items_cap, band_rows, halo;
   Ws ws;
   float* out;
 };
@@ -699,7 +750,13 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   const int nch = min(kCh, C - c0);
   const int part = blockIdx.z;
   constexpr int bins = kP * kP;
-  const int St = a.St, nblk = a.nblk, nsteps = a.nsteps;
+  const int St = a.St, nblk = a.nblk;
+  // rows this CTA streams: its band plus the window of the last item that starts in it; block indices below are
+  // RELATIVE to the band's first block (barrier slots and phases start at 0), ring slots stay absolute (the item
+  // records address them as y % ring rows)
+  const int y_begin = min(part * a.band_rows, H), y_end = min(H, y_begin + a.band_rows + a.halo);
+  const int b0 = y_begin / St;
+  const int nsteps = (y_end - y_begin + St - 1) / St;
   const int row_words = a.row_words;
   const float* fbase = feat_g + ((size_t)f * C + c0) * H * W;
   // dynamic shared: [ring (128-byte aligned)][record slots][bin-row tiles][pool][staging]
@@ -741,16 +798,19 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int plane0 = f * C + c0;
     const int pw_id = warp - kConsumers;                    // which producer
     constexpr int kChP = kCh / kProducers;                  // channels this producer repacks
-    auto fetch = [&](int y) {        // row y of the 32 channels -> staging buffer y % kStages
+    auto fetch = [&](int y) {        // row y of the 32 channels -> staging buffer (y - y_begin) % kStages
       if (pw_id == 0 && lane == 0) {
-        uint64_t* bar = &stg_bar[y % kStages];
+        const int sb = (y - y_begin) % kStages;
+        uint64_t* bar = &stg_bar[sb];
         mbar_expect_tx(bar, row_tx);
-        tma_load_2d(smem_u32(stg + (size_t)(y % kStages) * kCh * Ws), &tmap, (y * W) & ~3, plane0, bar);
+        tma_load_2d(smem_u32(stg + (size_t)sb * kCh * Ws), &tmap, (y * W) & ~3, plane0, bar);
       }
     };
-    for (int y = 0; y < kStages && y < H; ++y) fetch(y);
-    for (int y = 0; y < H; ++y) {
-      const int b = y / St, dy = y - b * St;
+    for (int y = y_begin; y < y_begin + kStages && y < y_end; ++y) fetch(y);
+    for (int y = y_begin; y < y_end; ++y) {
+      const int babs = y / St, dy = y - babs * St;
+      const int b = babs - b0;
+      const int sb = (y - y_begin) % kStages;
       if (dy == 0 && b >= nblk) {
         // the slot is free once every consumer warp works in a bucket beyond b - nblk
         for (;;) {
@@ -760,11 +820,11 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
           __nanosleep(64);
         }
       }
-      mbar_wait(&stg_bar[y % kStages], (uint32_t)((y / kStages) & 1));
+      mbar_wait(&stg_bar[sb], (uint32_t)(((y - y_begin) / kStages) & 1));
       const uint32_t sstep = (uint32_t)Ws * 4u, dstep = (uint32_t)a.lane_stride * 4u;
-      const uint32_t src = smem_u32(stg + (size_t)(y % kStages) * kCh * Ws) + (uint32_t)(lane + ((y * W) & 3)) * 4u +
+      const uint32_t src = smem_u32(stg + (size_t)sb * kCh * Ws) + (uint32_t)(lane + ((y * W) & 3)) * 4u +
                            (uint32_t)(pw_id * kChP) * sstep;
-      const uint32_t dst = ring_s + (uint32_t)((b % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
+      const uint32_t dst = ring_s + (uint32_t)((babs % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
                            (uint32_t)(pw_id * kChP) * dstep;
       // batches of 8 channels x up to 4 chunks (32 values per lane)
       const int ncg = (nchunk + 3) / 4, nbat = (kChP / 8) * ncg;
@@ -790,8 +850,8 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       }
       __syncwarp();
       if (kProducers > 1) asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");   // all producers done with the buffer
-      if (y + kStages < H) fetch(y + kStages);     // this staging buffer is free again
-      if (dy == St - 1 || y == H - 1) {
+      if (y + kStages < y_end) fetch(y + kStages);     // this staging buffer is free again
+      if (dy == St - 1 || y == y_end - 1) {
         if (lane == 0) mbar_arrive(&full_bar[b % nblk]);
       }
     }
@@ -837,9 +897,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     while (issued < nsteps) {
       const int b = issued;
       if (b >= nblk && !mbar_test(&done_bar[b % nblk], (uint32_t)(((b - nblk) / nblk) & 1))) break;
-      const int y0 = b * St;
-      const int prow = min(H, y0 + St) - y0;
-      const uint32_t blk = ring_s + (uint32_t)((b % nblk) * St) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u;
+      const int y0 = (b + b0) * St;
+      const int prow = min(y_end, y0 + St) - y0;
+      const uint32_t blk = ring_s + (uint32_t)(((b + b0) % nblk) * St) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u;
       const float* src0 = fbase + (size_t)y0 * W + lane;
       for (int pr = warp; pr < kCh * prow; pr += kWarps) {
         const int c = pr & 31, dy = pr >> 5;
@@ -932,7 +992,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     const int code = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.y));
     const int blocks = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__float_as_int(hdr.z));
     const int ph0 = code & 15, nph = (code >> 4) & 15, nrows = (code >> 8) & 255;
-    const int bucket = blocks & 0xFFFF, last_blk = blocks >> 16;
+    const int bucket = (blocks & 0xFFFF) - b0, last_blk = (blocks >> 16) - b0;
     float* o = out_g + ((size_t)r * C + c0) * bins + ph0 * kP;
     if (!((code >> 16) & 1)) {
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
@@ -1019,7 +1079,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
                            float scale, int S, int aligned, bool coop_fill, float* out, void* workspace,
                            size_t workspace_bytes, cudaStream_t st) {
   using namespace rows;
-  if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 24)) return B2D_ERR_UNSUPPORTED;
+  if (PH != kP || PW != kP || S < 1 || S > 2 || L.n >= (1 << 24) || H >= 2047) return B2D_ERR_UNSUPPORTED;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   const int per_frame = L.seg_count ? L.seg_stride : L.n;
@@ -1041,11 +1101,15 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   while (split < kMaxSplit && groups * split < 2 * kNumSMs) split *= 2;
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
-  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, p.nsteps, items_cap, ws, out};
+  // split > 1 (few frames): each of the `split` CTAs of a (frame, channel group) streams only its band of rows
+  const int band_rows = ceil_div(ceil_div(H, split), p.St) * p.St;
+  const int halo = (p.span_whole > p.span_max ? p.span_whole : p.span_max) - 1;
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, items_cap, band_rows, halo, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<dim3(ceil_div(per_frame, kPrepThreads), F), kPrepThreads, sizeof(int) * 3 * split * nb, st>>>( \
-        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, per_frame, split, ws); \
+    prep_kernel<SS><<<dim3(ceil_div(per_frame, kPrepWarps), F), kPrepThreads,                                        \
+                      sizeof(int) * (3 * split * nb + (items_cap <= kPrepKeyCache ? items_cap : 0)), st>>>( \
+        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, per_frame, split, band_rows, ws); \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
     fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap, feat, ws.records, L.rois, out);                    \

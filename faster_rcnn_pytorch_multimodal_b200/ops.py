@@ -106,8 +106,11 @@ def nms_sorted(boxes: torch.Tensor, thresh: float, max_keep: int = -1,
     keep = torch.empty(F, max(mk, 1), dtype=torch.int32, device=boxes.device)
     num = torch.zeros(F, dtype=torch.int32, device=boxes.device)
     if n > 0:
-        check(lib(boxes.device).b2d_nms_sorted(F, n, ptr(boxes), ptr(n_valid), float(thresh), mk, ptr(keep), ptr(num),
-                                   stream_ptr(boxes.device)), "b2d_nms_sorted")
+        L = lib(boxes.device)
+        nbytes = L.b2d_nms_workspace_bytes(F, mk)
+        ws = workspaces.get(boxes.device, "nms", nbytes) if nbytes else None
+        check(L.b2d_nms_sorted(F, n, ptr(boxes), ptr(n_valid), float(thresh), mk, ptr(keep), ptr(num), ptr(ws),
+                               int(nbytes), stream_ptr(boxes.device)), "b2d_nms_sorted")
     return keep, num
 
 

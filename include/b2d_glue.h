@@ -106,8 +106,12 @@ int b2d_proposal_debug_sorted(int num_frames, int n_loc, int num_anchors, int pr
  *   keep [F, max_keep] int32 positions (ascending), num_keep [F] int32.
  * The sweep stops once max_keep boxes are kept (== keep[:max_keep] of the full result).
  * ---------------------------------------------------------------------------------- */
+/* workspace: optional scratch of b2d_nms_workspace_bytes() bytes.  With it, calls of a few frames run one
+ * 16-CTA thread-block cluster per frame (chunked bitmask + one-warp sweep) instead of one CTA per frame. */
+size_t b2d_nms_workspace_bytes(int num_frames, int max_keep);
 int b2d_nms_sorted(int num_frames, int n, const float* boxes, const int32_t* n_valid, double thresh,
-                   int max_keep, int32_t* keep, int32_t* num_keep, void* stream);
+                   int max_keep, int32_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* Stable descending sort of scores (ties: lower index first); n <= b2d_max_pre_nms().
  *   order [F, n] int32.  Used by the nms() wrapper for unsorted input. */
