@@ -55,6 +55,10 @@
 // warp has just issued) and the read-back + transpose 17-24 us (49 dependent L2 loads stall one of only 8
 // consumer warps): 66 us/frame in total.  The scattered bin-row stores cost 2 us, not the 12 the round-1
 // knock-out build suggested; what the kernel waits for is the shared-memory pipe (0.7 wavefronts/clk).
+// Also measured and rejected: landing the TMA box in the ring slot itself and repacking it IN PLACE (no staging
+// buffer: 13 ring rows instead of 11, window 10 + slack 3, every free slot with a copy in flight, the two
+// producers on alternate rows): 37.2 us/frame against 35.8 - a row repacked by one warp takes twice as long to
+// publish, and the deeper ring buys nothing because the consumers are not waiting for slack.
 //
 // Two things ptxas must be told (each cost 10 % when missed): (1) every branch on a warp-uniform value
 // goes through a warp reduction (CREDUX -> uniform register); one branch it takes for divergent - the
