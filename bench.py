@@ -230,9 +230,9 @@ class Harness:
         return [float(v) for v in t]
 
     def gather_records(self, rec):
-        """The path's only collective: end-of-stream gather of the per-frame records (stream.gather_detections)."""
-        if self.dist is not None:
-            self.dist.all_gather([torch.empty_like(rec) for _ in range(self.world)], rec)
+        """The path's only collective: end-of-stream all_gather of the fixed-size per-frame records."""
+        from faster_rcnn_pytorch_multimodal_b200 import stream
+        return stream.gather_detections(rec, rec.shape[0]) if self.dist is not None else rec
 
     def time_steps(self, step, record_fn=None, sample_clocks=True):
         """W warm-ups, barrier + sync, exactly K steps between CUDA events, the gather, barrier + sync; max over ranks."""
@@ -563,7 +563,9 @@ def run_inference(args, cfg):
         crop_events.append((e0, e1))
         return rois, scores, num
 
-    record = lambda o: torch.cat((o[0].view(F, -1), o[1], o[2].view(F, 1).float()), dim=1)
+    from faster_rcnn_pytorch_multimodal_b200 import stream
+    frame_ids = list(range(rank * F, rank * F + F))
+    record = lambda o: stream.pack_records(o[0], o[1], o[2], frame_ids)      # proposal-stage records: no head here
     elapsed_ms, launches, clocks, (rois, scores, num) = h.time_steps(step, record)
     crop_ms = float(np.mean([a.elapsed_time(b) for a, b in crop_events[-args.steps:]]))
     (crop_ms,) = h.max_over_ranks(crop_ms)
@@ -952,7 +954,10 @@ def run_mc(args, cfg):
             max_out=cfg["max_dets"])
         return out, dets, counts, o_ur, o_uc
 
-    record = lambda o: torch.cat((o[1].reshape(F, -1), o[2].float().reshape(F, -1)), 1)
+    from faster_rcnn_pytorch_multimodal_b200 import stream
+    frame_ids = list(range(rank * F, rank * F + F))
+    # the wire format of SURVEY §8e: padded final-detection records (box, score, gathered uncertainties) + counts
+    record = lambda o: stream.pack_detection_records(o[1], o[2], frame_ids, o[3], o[4])
     elapsed_ms, launches, clocks, (out, dets, counts, o_ur, o_uc) = h.time_steps(step, record)
     value = world * F * args.steps / (elapsed_ms * 1e-3)
     # parity gate: frames 0 and F-1 against the oracle chain

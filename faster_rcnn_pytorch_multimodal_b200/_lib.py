@@ -31,7 +31,8 @@ PROTOTYPES = {
     "b2d_proposal_debug_sorted": (I, [I, I, I, I, I, _v, _f, _f, _i, _v]),
     "b2d_nms_workspace_bytes": (SZ, [I, I]),
     "b2d_nms_sorted": (I, [I, I, _f, _i, F64, I, _i, _i, _v, SZ, _v]),
-    "b2d_argsort_desc": (I, [I, I, _f, _i, _v]),
+    "b2d_argsort_workspace_bytes": (SZ, [I, I]),
+    "b2d_argsort_desc": (I, [I, I, _f, _i, _v, SZ, _v]),
     "b2d_roi_align_workspace_bytes": (SZ, [I, I, I, I, I, I]),
     "b2d_roi_align_forward": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, _f, _v, SZ, _v]),
     "b2d_roi_align_forward_route": (I, [I, I, I, I, _f, _f, I, _i, I, _i, I, I, I, F32, I, I, I, _f, _v, SZ, _v]),

@@ -32,6 +32,7 @@ struct ProposalWs {
   int32_t* num_keep;      // [F]
   uint32_t* rank;         // [F][kMaxSortElems]: rank-sort counters (few-frame path)
   void* nms_kept;         // kept boxes of the cluster NMS (few-frame path)
+  uint64_t* cand2;        // [F][N]: second buffer of the chunk-sort + merge path (pre_nms > kMaxSortElems only)
   size_t bytes;
 };
 
@@ -73,6 +74,7 @@ static ProposalWs carve(void* base, int F, int N, int pre, int post) {
   w.rank = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)(F <= kRankMaxFrames ? F : 0) * kMaxSortElems));
   const size_t nk = nms_cluster_workspace_bytes(F, mo);
   w.nms_kept = nk ? take(nk) : nullptr;
+  w.cand2 = k > kMaxSortElems ? reinterpret_cast<uint64_t*>(take(sizeof(uint64_t) * (size_t)F * N)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -449,6 +451,107 @@ __global__ void __launch_bounds__(256) rank_scatter_kernel(DecodeArgs a, const u
   oi[r] = idx;
 }
 
+// ---------------------------------------------------------------------------------------
+// Lists longer than the in-CTA capacity (pre_nms_topN > 16384 or <= 0, argsort / nms of more than 16384 boxes):
+// bitonic-sort chunks of kMaxSortElems in shared memory, then merge runs pairwise.  A merge pass is one thread per
+// element: its position in the merged run = its position in its own run + the number of elements of the partner
+// run that precede it (binary search; composites are unique, so there are no ties to break).
+__global__ void __launch_bounds__(1024) chunk_sort_kernel(uint64_t* __restrict__ keys_all, const uint32_t* __restrict__ sel,
+                                                          int stride, int n_fixed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int f = blockIdx.y;
+  const int m = sel ? (int)sel[f * 4 + 1] : n_fixed;
+  const int c0 = blockIdx.x * kMaxSortElems;
+  if (c0 >= m) return;
+  uint64_t* g = keys_all + (size_t)f * stride + c0;
+  const int cnt = min(kMaxSortElems, m - c0);
+  int n_pad = 2;
+  while (n_pad < cnt) n_pad <<= 1;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = i < cnt ? g[i] : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(keys, n_pad);
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) g[i] = keys[i];
+}
+
+__global__ void __launch_bounds__(256) merge_pass_kernel(const uint64_t* __restrict__ src_all, uint64_t* __restrict__ dst_all,
+                                                         const uint32_t* __restrict__ sel, int stride, int n_fixed,
+                                                         int run) {
+  const int f = blockIdx.y;
+  const int m = sel ? (int)sel[f * 4 + 1] : n_fixed;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t* src = src_all + (size_t)f * stride;
+  uint64_t* dst = dst_all + (size_t)f * stride;
+  const int r = i / run, own = i - r * run;
+  const int p0 = (r ^ 1) * run, p1 = min(p0 + run, m);        // partner run
+  const uint64_t v = src[i];
+  int cnt = 0;
+  if (p0 < m) {
+    // descending runs: number of partner elements greater than v
+    int lo = p0, hi = p1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (src[mid] > v) lo = mid + 1; else hi = mid;
+    }
+    cnt = lo - p0;
+  }
+  dst[(size_t)(r & ~1) * run + own + cnt] = v;
+}
+
+// sorted composites -> the first k rows of the sorted list, decoded + clipped (rows k .. k_cap-1 zero-filled)
+__global__ void __launch_bounds__(256) sorted_decode_kernel(DecodeArgs a, const uint32_t* __restrict__ sel,
+                                                            const uint64_t* __restrict__ sorted_all,
+                                                            float* __restrict__ sorted_boxes,
+                                                            float* __restrict__ sorted_scores,
+                                                            int32_t* __restrict__ sorted_index,
+                                                            int32_t* __restrict__ n_sorted, int k_cap, int decode) {
+  const int f = blockIdx.y;
+  const int m = (int)sel[f * 4 + 1];
+  const int k = min((int)sel[f * 4 + 2], m);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) n_sorted[f] = k;
+  if (i >= k_cap) return;
+  float box[4] = {0.f, 0.f, 0.f, 0.f};
+  float sc = 0.f;
+  int idx = 0;
+  if (i < k) {
+    idx = (int)composite_index(sorted_all[(size_t)f * a.N + i]);
+    sc = fg_score(a.cls_prob, f, a.n_loc, a.A, idx);
+    if (decode) {
+      const float* anc = a.anchors + (size_t)idx * 4;
+      const float* d = a.bbox_pred + ((size_t)f * a.N + idx) * 4;
+      const float an[4] = {__ldg(anc), __ldg(anc + 1), __ldg(anc + 2), __ldg(anc + 3)};
+      const float dd[4] = {__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3)};
+      decode_clip(an, dd, a.info + f * 7, box);
+    }
+  }
+  float* ob = sorted_boxes + ((size_t)f * k_cap + i) * 4;
+  ob[0] = box[0], ob[1] = box[1], ob[2] = box[2], ob[3] = box[3];
+  sorted_scores[(size_t)f * k_cap + i] = sc;
+  sorted_index[(size_t)f * k_cap + i] = idx;
+}
+
+// Sorts the first m (device count, or n_fixed) composites of every frame's list, descending; returns the buffer
+// that holds the result (a or b).
+static int sort_large(int F, int n_max, int stride, uint64_t* a, uint64_t* b, const uint32_t* sel, int n_fixed,
+                      cudaStream_t st, uint64_t** result) {
+  const size_t smem = sizeof(uint64_t) * kMaxSortElems;
+  B2D_CUDA(cudaFuncSetAttribute(chunk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chunk_sort_kernel<<<dim3(ceil_div(n_max, kMaxSortElems), F), 1024, smem, st>>>(a, sel, stride, n_fixed);
+  B2D_LAUNCHED();
+  uint64_t *src = a, *dst = b;
+  for (long long run = kMaxSortElems; run < n_max; run *= 2) {
+    merge_pass_kernel<<<dim3(ceil_div(n_max, 256), F), 256, 0, st>>>(src, dst, sel, stride, n_fixed, (int)run);
+    B2D_LAUNCHED();
+    uint64_t* t = src;
+    src = dst;
+    dst = t;
+  }
+  *result = src;
+  return B2D_OK;
+}
+
 // keep positions -> output rows (proposal_layer.py:48-55); pads the tail with zeros.
 __global__ void __launch_bounds__(256) proposal_gather_kernel(
     const float* __restrict__ sorted_boxes, const float* __restrict__ sorted_scores,
@@ -542,6 +645,16 @@ static int select_sort(int F, int n_loc, int A, const float* cls_prob, const flo
   const size_t smem = sizeof(uint64_t) * kMaxSortElems;
   B2D_CUDA(cudaFuncSetAttribute(sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DecodeArgs a{cls_prob, bbox_pred, info, anchors, n_loc, A, N};
+  if (k > kMaxSortElems) {
+    // more boxes wanted than one CTA can sort: chunk sort + merge passes over the whole candidate list
+    uint64_t* sorted = nullptr;
+    const int rc = sort_large(F, N, N, w.cand, w.cand2, w.sel, 0, st, &sorted);
+    if (rc != B2D_OK) return rc;
+    sorted_decode_kernel<<<dim3(ceil_div(k, 256), F), 256, 0, st>>>(a, w.sel, sorted, w.sorted_boxes, w.sorted_scores,
+                                                                   w.sorted_index, w.n_sorted, k, decode);
+    B2D_LAUNCHED();
+    return B2D_OK;
+  }
   const bool few = F <= kRankMaxFrames;
   if (few) {
     // the candidate count is only known on the device: size the grid for the largest list the path takes
@@ -587,7 +700,6 @@ extern "C" int b2d_proposal(int F, int n_loc, int A, const float* cls_prob, cons
   if ((long long)n_loc * A > 0x7FFFFFFFll / 8) return B2D_ERR_UNSUPPORTED;
   const int N = n_loc * A;
   const int k = top_k_of(N, pre_nms);
-  if (k > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
   const int mo = max_out_of(N, pre_nms, post_nms);
   ProposalWs w = carve(workspace, F, N, pre_nms, post_nms);
   if (!workspace || workspace_bytes < w.bytes) return B2D_ERR_WORKSPACE;
@@ -613,7 +725,6 @@ extern "C" int b2d_proposal_top(int F, int n_loc, int A, const float* cls_prob, 
     return B2D_ERR_INVALID_ARG;
   const int N = n_loc * A;
   if (top_n > N) return B2D_ERR_UNSUPPORTED;  // the reference's random-fill branch stays on the host
-  if (top_n > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
   ProposalWs w = carve(workspace, F, N, top_n, top_n);
   if (!workspace || workspace_bytes < w.bytes) return B2D_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
@@ -646,10 +757,41 @@ extern "C" int b2d_proposal_debug_sorted(int F, int n_loc, int A, int pre_nms, i
   return B2D_OK;
 }
 
-extern "C" int b2d_argsort_desc(int F, int n, const float* scores, int32_t* order, void* stream) {
+namespace b2d {
+__global__ void __launch_bounds__(256) argsort_keys_kernel(const float* __restrict__ scores, int n, uint64_t* __restrict__ keys) {
+  const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[(size_t)f * n + i] = composite_key(score_key(scores[(size_t)f * n + i]), (uint32_t)i);
+}
+__global__ void __launch_bounds__(256) argsort_index_kernel(const uint64_t* __restrict__ keys, int n, int32_t* __restrict__ order) {
+  const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[(size_t)f * n + i] = (int32_t)composite_index(keys[(size_t)f * n + i]);
+}
+}  // namespace b2d
+
+extern "C" size_t b2d_argsort_workspace_bytes(int F, int n) {
+  if (F <= 0 || n <= kMaxSortElems) return 0;
+  return 2 * align_up(sizeof(uint64_t) * (size_t)F * n, 256);
+}
+
+extern "C" int b2d_argsort_desc(int F, int n, const float* scores, int32_t* order, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   if (F <= 0 || n < 0 || !scores || !order) return B2D_ERR_INVALID_ARG;
   if (n == 0) return B2D_OK;
-  if (n > kMaxSortElems) return B2D_ERR_UNSUPPORTED;
+  if (n > kMaxSortElems) {
+    const size_t half = align_up(sizeof(uint64_t) * (size_t)F * n, 256);
+    if (!workspace || workspace_bytes < 2 * half) return B2D_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    uint64_t* a = static_cast<uint64_t*>(workspace);
+    uint64_t* b = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + half);
+    argsort_keys_kernel<<<dim3(ceil_div(n, 256), F), 256, 0, st>>>(scores, n, a);
+    B2D_LAUNCHED();
+    uint64_t* sorted = nullptr;
+    const int rc = sort_large(F, n, n, a, b, nullptr, n, st, &sorted);
+    if (rc != B2D_OK) return rc;
+    argsort_index_kernel<<<dim3(ceil_div(n, 256), F), 256, 0, st>>>(sorted, n, order);
+    B2D_LAUNCHED();
+    return B2D_OK;
+  }
   const size_t smem = sizeof(uint64_t) * kMaxSortElems;
   B2D_CUDA(cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int n_pad = 2;

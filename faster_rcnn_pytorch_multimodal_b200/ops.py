@@ -121,7 +121,11 @@ def argsort_desc(scores: torch.Tensor) -> torch.Tensor:
     F, n = scores.shape
     order = torch.empty(F, n, dtype=torch.int32, device=scores.device)
     if n > 0:
-        check(lib(scores.device).b2d_argsort_desc(F, n, ptr(scores), ptr(order), stream_ptr(scores.device)), "b2d_argsort_desc")
+        L = lib(scores.device)
+        nbytes = L.b2d_argsort_workspace_bytes(F, n)
+        ws = workspaces.get(scores.device, "argsort", nbytes) if nbytes else None
+        check(L.b2d_argsort_desc(F, n, ptr(scores), ptr(order), ptr(ws), int(nbytes), stream_ptr(scores.device)),
+              "b2d_argsort_desc")
     return order
 
 
@@ -134,8 +138,6 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     n = boxes.shape[0]
     if n == 0:
         return torch.empty(0, dtype=torch.int64, device=boxes.device)
-    if n > lib().b2d_max_pre_nms():
-        raise _lib.B2DError(f"nms: n={n} exceeds the in-CTA sort capacity {lib().b2d_max_pre_nms()}")
     order = argsort_desc(scores.reshape(1, n))[0].long()
     keep, num = nms_sorted(f32c(boxes)[order].unsqueeze(0), iou_threshold)
     return order[keep[0, :int(num.item())].long()]

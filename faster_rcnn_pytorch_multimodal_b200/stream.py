@@ -44,6 +44,47 @@ def unpack_records(rec: torch.Tensor, M: int) -> List[Tuple[int, torch.Tensor, t
     return out
 
 
+def pack_detection_records(dets: torch.Tensor, counts: torch.Tensor, frame_ids: Sequence[int],
+                           uc_row: Optional[torch.Tensor] = None, uc_cls: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The wire format of the end-of-stream gather: one fixed-size fp32 record per frame holding what
+    ``ops.final_detections`` emits - dets [F,K,D,E+1] (box, score), counts [F,K], and the gathered uncertainty
+    columns uc_row [F,K,D,U] / uc_cls [F,K,D,U2*E] in the reference's hstack order (model/test.py:260-270) ->
+    [F, 2 + K + K*D*(E+1+U+U2*E)].  Column 0 is the frame id, column 1 the row width per detection."""
+    F, K, D, E1 = dets.shape
+    parts = [dets]
+    if uc_row is not None:
+        parts.append(uc_row)
+    if uc_cls is not None:
+        parts.append(uc_cls)
+    rows = torch.cat(parts, dim=3)                                     # [F,K,D,width]: bbox | score | uncertainties
+    width = rows.shape[3]
+    ids = torch.as_tensor(list(frame_ids), dtype=torch.float32, device=dets.device).view(F, 1)
+    return torch.cat((ids, torch.full((F, 1), float(width), device=dets.device), counts.view(F, K).float(),
+                      rows.reshape(F, K * D * width)), dim=1)
+
+
+def unpack_detection_records(rec: torch.Tensor, num_classes: int, num_frames: int):
+    """Gathered records -> the reference's ``all_boxes[cls][frame]`` (model/test.py:162-163,226): a list over
+    classes of lists over frames of numpy arrays [m, E+1+uncertainties] (``np.empty(0)`` where a class has no
+    detection, as the reference stores it).  Class 0 (background) stays empty lists."""
+    import numpy as np
+    K = num_classes
+    all_boxes = [[np.empty(0) for _ in range(num_frames)] for _ in range(K)]
+    rec = rec.cpu()
+    for row in rec:
+        fid = int(row[0].item())
+        if fid < 0 or fid >= num_frames:
+            continue
+        width = int(row[1].item())
+        counts = row[2:2 + K].to(torch.int64)
+        body = row[2 + K:].view(K, -1, width)
+        for j in range(1, K):
+            m = int(counts[j])
+            if m > 0:
+                all_boxes[j][fid] = body[j, :m].numpy().copy()
+    return all_boxes
+
+
 def gather_detections(local_records: torch.Tensor, max_frames_per_rank: int,
                       group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """all_gather of per-rank record blocks, padded to ``max_frames_per_rank`` rows (frame id -1);

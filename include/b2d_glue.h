@@ -45,7 +45,8 @@ const char* b2d_status_string(int status);
 int b2d_last_cuda_error(void);
 /* Number of kernels this library launched since load (all threads). */
 uint64_t b2d_launch_count(void);
-/* Upper limits compiled into the select/sort kernel. */
+/* Capacity of the in-CTA sort: up to this many boxes (pre_nms_topN, argsort n) sort in shared memory; more take
+ * the chunk-sort + merge path (no upper limit). */
 int b2d_max_pre_nms(void);
 
 /* ------------------------------------------------------------------------------------
@@ -113,9 +114,12 @@ int b2d_nms_sorted(int num_frames, int n, const float* boxes, const int32_t* n_v
                    int max_keep, int32_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
                    void* stream);
 
-/* Stable descending sort of scores (ties: lower index first); n <= b2d_max_pre_nms().
- *   order [F, n] int32.  Used by the nms() wrapper for unsorted input. */
-int b2d_argsort_desc(int num_frames, int n, const float* scores, int32_t* order, void* stream);
+/* Stable descending sort of scores (ties: lower index first), order [F, n] int32.  Used by the nms() wrapper for
+ * unsorted input.  n <= b2d_max_pre_nms() sorts in one CTA per frame and needs no workspace; longer lists are
+ * chunk-sorted and merged in b2d_argsort_workspace_bytes() bytes of scratch. */
+size_t b2d_argsort_workspace_bytes(int num_frames, int n);
+int b2d_argsort_desc(int num_frames, int n, const float* scores, int32_t* order, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * RoIAlign forward / backward (torchvision.ops.roi_align semantics, NCHW fp32).

@@ -159,6 +159,21 @@ def test_nms_vs_oracle_bit_exact(n, thr):
         assert np.array_equal(O.nms_greedy_np(b.numpy(), s.numpy(), thr), want.numpy())
 
 
+@pytest.mark.parametrize("n,ties", [(16385, False), (20000, True), (50000, False)])
+def test_nms_and_argsort_beyond_in_cta_capacity(n, ties):
+    """More boxes than the in-CTA sort holds (16 384): chunk sort + merge passes, then the same NMS sweep.
+    torchvision has no such limit (proposal_layer.py:46 with RPN_PRE_NMS_TOP_N <= 0 on a Waymo frame)."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    b, s = clustered_boxes(300 + n, n, n_centers=400)
+    if ties:
+        s = (s * 64).round() / 64                        # hundreds of equal scores: index order decides
+    order = ops.argsort_desc(s.view(1, n).to(dev()))[0]
+    assert torch.equal(order.cpu().long(), torch.argsort(s, descending=True, stable=True))
+    want = O.nms_greedy_np(b.numpy(), s.numpy(), 0.7) if ties else O.nms(b, s, 0.7).numpy()
+    got = ops.nms(b.to(dev()), s.to(dev()), 0.7)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 def test_nms_ties_empty_and_early_stop():
     from faster_rcnn_pytorch_multimodal_b200 import ops
     b, s = clustered_boxes(5, 3000)
@@ -260,6 +275,20 @@ def test_proposal_layer_image_configs(name, Hf, Wf, W, H, key, pre, post):
     anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0])
     info = np.array([0, W, 0, H, 0, 0, 1.0], dtype=np.float32)
     _run_proposal_vs_oracle(prob, deltas, info, anchors, None, A, key, pre, post)
+
+
+@pytest.mark.parametrize("name,Hf,Wf,W,H,pre,post", [
+    ("waymo_pre20000", 80, 120, 1920, 1280, 20000, 2000),     # two sort chunks + one merge pass
+    ("kitti_all", 24, 78, 1242, 375, -1, 300),                # pre_nms <= 0: every anchor is ranked (N = 46 800)
+    ("waymo_pre50000", 80, 120, 1920, 1280, 50000, 300),      # four chunks, two merge passes, ragged last chunk
+])
+def test_proposal_layer_pre_nms_beyond_in_cta_capacity(name, Hf, Wf, W, H, pre, post):
+    """proposal_layer.py:39-41 takes any RPN_PRE_NMS_TOP_N (<= 0 keeps all N); the in-CTA sort holds 16 384."""
+    A = 25
+    prob, deltas = synth_rpn(17, Hf, Wf, A)
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0])
+    info = np.array([0, W, 0, H, 0, 0, 1.0], dtype=np.float32)
+    _run_proposal_vs_oracle(prob, deltas, info, anchors, None, A, "TEST", pre, post)
 
 
 def test_proposal_layer_fpn_p2_scale():

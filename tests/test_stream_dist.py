@@ -30,6 +30,26 @@ def test_pack_unpack_roundtrip():
     assert torch.equal(got[1][1], rois[1, :2]) and torch.equal(got[1][2], scores[1, :2]) and got[2][1].shape[0] == 0
 
 
+def test_detection_records_rebuild_all_boxes():
+    """final_detections' padded outputs -> wire records -> the reference's all_boxes[cls][frame]."""
+    import numpy as np
+    F, K, D, E = 3, 3, 4, 7
+    g = torch.Generator().manual_seed(1)
+    dets = torch.rand(F, K, D, E + 1, generator=g)
+    uc_row = torch.rand(F, K, D, 2, generator=g)
+    uc_cls = torch.rand(F, K, D, E, generator=g)
+    counts = torch.tensor([[0, 2, 0], [0, 4, 1], [0, 0, 0]], dtype=torch.int32)
+    rec = stream.pack_detection_records(dets, counts, [5, 0, 2], uc_row, uc_cls)
+    assert rec.shape == (F, 2 + K + K * D * (E + 1 + 2 + E))
+    allrec = stream.gather_detections(rec, 4)
+    ab = stream.unpack_detection_records(allrec, K, 6)
+    assert len(ab) == K and all(len(c) == 6 for c in ab)
+    assert ab[1][5].shape == (2, E + 1 + 2 + E)
+    assert np.array_equal(ab[1][5][:, :E + 1], dets[0, 1, :2].numpy()) and np.array_equal(ab[1][5][:, E + 1:E + 3], uc_row[0, 1, :2].numpy())
+    assert np.array_equal(ab[2][0], torch.cat((dets[1, 2, :1], uc_row[1, 2, :1], uc_cls[1, 2, :1]), 1).numpy())
+    assert ab[1][2].size == 0 and ab[2][5].size == 0 and ab[0][0].size == 0
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
