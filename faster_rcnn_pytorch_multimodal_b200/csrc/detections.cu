@@ -17,8 +17,9 @@
 
 namespace b2d {
 
-constexpr int kDetThreads = 256;
-constexpr int kDetMaxRois = 1024;
+constexpr int kDetThreads = 256;      // up to 1024 RoIs per frame (the test configurations: 300)
+constexpr int kDetThreadsBig = 1024;  // more (cfg.TRAIN.RPN_POST_NMS_TOP_N = 2000 RoIs through filter_and_draw_prep)
+constexpr int kDetMaxRois = 4096;     // shared-memory staging: 29 bytes per (padded) RoI, 116 KB at the limit
 
 __device__ __forceinline__ bool det_iou_exceeds(const float4 a, const float4 b, const float thr_f) {
   const float w = fmaxf(0.0f, fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
@@ -47,20 +48,22 @@ struct DetArgs {
   int32_t* counts;          // [F, K]
 };
 
-__global__ void __launch_bounds__(kDetThreads) final_detections_kernel(DetArgs a) {
-  __shared__ unsigned long long s_key[kDetMaxRois];
-  __shared__ float4 s_box[kDetMaxRois];      // NMS boxes in sorted order
-  __shared__ unsigned char s_dead[kDetMaxRois];
-  __shared__ int s_keep[kDetMaxRois];
+static size_t det_smem_bytes(int n_pad) { return (size_t)n_pad * (16 + 8 + 4 + 1); }
+
+__global__ void __launch_bounds__(kDetThreadsBig) final_detections_kernel(DetArgs a, int n_pad) {
+  extern __shared__ __align__(16) unsigned char det_smem[];
+  float4* s_box = reinterpret_cast<float4*>(det_smem);                                     // NMS boxes in sorted order
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_box + n_pad);
+  int* s_keep = reinterpret_cast<int*>(s_key + n_pad);
+  unsigned char* s_dead = reinterpret_cast<unsigned char*>(s_keep + n_pad);
   __shared__ int s_n, s_m;
+  const int kDetThreads = (int)blockDim.x;
   const int c = blockIdx.x + 1, f = blockIdx.y;
   const int tid = threadIdx.x;
   const int R = a.R, K = a.K, E = a.E;
   const int n = a.num_rois ? min(a.num_rois[f], R) : R;
   const float* score = a.cls_score + (size_t)f * R * K + c;
   const float* boxes = a.pred_boxes + (size_t)f * R * K * E + (size_t)c * E;
-  int n_pad = 1;
-  while (n_pad < R) n_pad <<= 1;
   if (tid == 0) s_n = 0;
   __syncthreads();
   // 1-2. candidates as composite keys (score desc, index asc); non-candidates sort last (key 0)
@@ -204,7 +207,12 @@ extern "C" int b2d_final_detections(int F, int R, int K, int E, const float* cls
             score_thresh, float_floor_of(nms_thresh), dets, det_roi, n_uc_row > 0 ? out_uc_row : nullptr,
             n_uc_cls > 0 ? out_uc_cls : nullptr, counts};
   dim3 grid(K - 1, F);
-  final_detections_kernel<<<grid, kDetThreads, 0, st>>>(a);
+  int n_pad = 1;
+  while (n_pad < R) n_pad <<= 1;
+  const size_t smem = det_smem_bytes(n_pad);
+  if (smem > 48 * 1024)
+    B2D_CUDA(cudaFuncSetAttribute(final_detections_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  final_detections_kernel<<<grid, R > 1024 ? kDetThreadsBig : kDetThreads, smem, st>>>(a, n_pad);
   B2D_LAUNCHED();
   return B2D_OK;
 }

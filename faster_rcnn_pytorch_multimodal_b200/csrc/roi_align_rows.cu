@@ -83,10 +83,22 @@ namespace rows {
 #define B2D_POOL 2
 #endif
 #ifndef B2D_SLACK
-#define B2D_SLACK 2
+#define B2D_SLACK 1
+#endif
+#ifndef B2D_SLACK_BIG
+#define B2D_SLACK_BIG 3
+#endif
+#ifndef B2D_WARPS
+#define B2D_WARPS 12
+#endif
+#ifndef B2D_POLL_NS
+#define B2D_POLL_NS 64
+#endif
+#ifndef B2D_WAIT_NS
+#define B2D_WAIT_NS 0
 #endif
 
-constexpr int kWarps = 12;          // 10 consumers + 2 producers (12 measured 1.2 % faster than 10: 35.8 vs 36.3 us/frame)
+constexpr int kWarps = B2D_WARPS;          // 10 consumers + 2 producers (12 measured 1.2 % faster than 10: 35.8 vs 36.3 us/frame)
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
 constexpr int kP = 7;              // PH = PW = 7
@@ -97,6 +109,7 @@ constexpr int kXVec = 11;          // float4 holding 14 column taps {xo, hx, lx}
 constexpr int kRowVec0 = 1 + kXVec;
 constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each streams one band of rows
+constexpr int kRowBlkShift = 18;   // row entries: ring byte offset (< 227 KB) in the low bits, block of the row above
 
 constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps
 constexpr int kTileWords = kCh * kP * kP;
@@ -138,7 +151,7 @@ static Plan make_plan(int H, int W, bool allow_tma) {
     if (St < 1) St = 1;
     Rr -= Rr % St;                                   // blocks of St rows never wrap inside the ring
     const int nblk = Rr / St;
-    const int slack = nblk >= 12 ? 3 : (nblk >= 8 ? B2D_SLACK : 1);
+    const int slack = nblk >= 12 ? B2D_SLACK_BIG : (nblk >= 8 ? B2D_SLACK : 1);
     p.Rr = Rr; p.St = St; p.nblk = nblk; p.nbk = nblk - slack;
     p.span_max = (p.nbk - 1) * St + 1;
     p.nsteps = ceil_div(H, St);
@@ -402,7 +415,7 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
         }
         if (lane >= kRowVec0) {
           int off = 0;
-          if (y >= 0) off = (Rr == H ? y : y % Rr) * row_bytes;
+          if (y >= 0) off = ((Rr == H ? y : y % Rr) * row_bytes) | ((y / St) << kRowBlkShift);   // ring byte offset | block of the row
           out = half == 0 ? make_float4(__int_as_float(off), wv[1], wv[2], wv[3]) : make_float4(wv[0], wv[1], wv[2], wv[3]);
         }
         rec[lane] = out;
@@ -548,8 +561,8 @@ __device__ __forceinline__ float lds_at(uint32_t addr) {
 // One item: nph = NPH bin-rows of one RoI for this lane's channel.
 // NPH is the variant (2, 4 or 7 accumulator rows), nph <= NPH the bin-rows the item really has: the rows in
 // between carry zero weights and are not stored.
-template <int NPH, int S, bool POOL>
-__device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
+template <int NPH, int S, bool POOL, class Landed>
+__device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
                                          const int (&ooff)[kP], unsigned omask,
                                          float* __restrict__ pool, int* locks, int warp, bool tile_out, int& held) {
@@ -679,7 +692,9 @@ __device__ __forceinline__ void run_item(const float4* __restrict__ slot, int nr
 #pragma unroll 1
   for (int i = 0; i < nrows; ++i) {
     const float4 f0 = e0, f1 = e1;
-    const uint32_t ro = row_off(f0);
+    const uint32_t rv = row_off(f0);
+    const uint32_t ro = rv & ((1u << kRowBlkShift) - 1u);
+    wait_row((int)(rv >> kRowBlkShift));        // the row's block has landed (a test on a uniform counter unless it is new)
     e0 = slot[kRowVec0 + (i + 1) * RV];
     if (RV == 2) e1 = slot[kRowVec0 + (i + 1) * RV + 1];
     float t[NT];
@@ -821,7 +836,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
           int pr = lane < kConsumers ? *reinterpret_cast<volatile int*>(&s_progress[lane]) : 0x7fffffff;
           pr = (int)__reduce_min_sync(0xffffffffu, (unsigned)pr);
           if (pr > b - nblk) break;
-          __nanosleep(64);
+          __nanosleep(B2D_POLL_NS);
         }
       }
       mbar_wait(&stg_bar[sb], (uint32_t)(((y - y_begin) / kStages) & 1));
@@ -918,7 +933,11 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   };
   auto wait_on = [&](uint64_t* bar, uint32_t parity) {
     if (FILL) {
-      mbar_wait(bar, parity);
+      if (B2D_WAIT_NS > 0) {
+        while (!mbar_test(bar, parity)) __nanosleep(B2D_WAIT_NS);
+      } else {
+        mbar_wait(bar, parity);
+      }
     } else {
       while (!mbar_test(bar, parity)) pump();
     }
@@ -930,6 +949,24 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
     // parity test is valid as long as the block one phase earlier (b - nblk) is known to have landed
     if (FILL && upto > landed && upto - 1 - nblk < landed) landed = upto - 1;
     for (; landed < upto; ++landed) wait_on(&full_bar[landed % nblk], (uint32_t)((landed / nblk) & 1));
+  };
+  // TMA fill: an item does not wait for its window.  Each row entry names its block and the row loop waits for a
+  // block the first time this warp meets it, so an item starts as soon as its first row is there and consumes the
+  // rest as the fill delivers them (blocks land in order; `landed` walks them one by one, which also keeps every
+  // parity test within one phase of the barrier).
+  int land_slot = 0;
+  uint32_t land_phase = 0;
+  auto wait_row = [&](int blk_abs) {
+    if (!FILL) return;
+    const int blk = blk_abs - b0;
+    while (landed <= blk) {
+      mbar_wait(&full_bar[land_slot], land_phase);
+      ++landed;
+      if (++land_slot == nblk) {
+        land_slot = 0;
+        land_phase ^= 1u;
+      }
+    }
   };
   // mbarrier parity waits are only meaningful within one phase of the barrier's current phase, so
   // every warp walks both barrier arrays strictly in order: it observes block j before it releases
@@ -1015,8 +1052,8 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       // release the buckets this warp has left behind, then make sure the item's blocks have landed
       // (only the blocks the item reads have to be there, not its whole window)
       release(bucket);
-      observe(min(last_blk + 1, nsteps));
-#define B2D_RUN(N) run_item<N, S, FILL>(slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
+      if (!FILL) observe(min(last_blk + 1, nsteps));
+#define B2D_RUN(N) run_item<N, S, FILL>(wait_row, slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
       if (nph <= 2) B2D_RUN(2);
       else if (nph <= 4) B2D_RUN(4);
       else B2D_RUN(7);

@@ -335,7 +335,7 @@ int b2d_bev_rasterize(int num_points, int num_feat, const float* points, float x
  *   uc_cls [F,R,n_uc_cls,K*E] per-class-box columns (bbox variances) are gathered alongside.
  * Outputs, padded to max_out rows per (frame, class) with zeros / -1:
  *   dets [F,K,max_out,E+1] = box, score; det_roi [F,K,max_out] source roi; counts [F,K];
- *   out_uc_row [F,K,max_out,n_uc_row]; out_uc_cls [F,K,max_out,n_uc_cls*E].  R <= 1024.
+ *   out_uc_row [F,K,max_out,n_uc_row]; out_uc_cls [F,K,max_out,n_uc_cls*E].  R <= 4096 (shared-memory staging of one frame x class).
  * ---------------------------------------------------------------------------------- */
 int b2d_final_detections(int num_frames, int num_rois_max, int num_classes, int num_elem,
                          const float* cls_score, const float* pred_boxes, const int32_t* num_rois,

@@ -638,6 +638,66 @@ def test_proposal_target_intended_bg_mode_vs_oracle(golden):
     assert got[0].shape[0] == 256 and int((got[0] == 0).sum()) >= 192
 
 
+def test_anchor_target_clobber_positives_vs_oracle():
+    """cfg.TRAIN.RPN_CLOBBER_POSITIVES = True (anchor_target_layer.py:74-92): the negative-overlap rule is applied
+    AFTER the positives, so a per-GT best anchor below RPN_NEGATIVE_OVERLAP ends up background."""
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.anchor_target_layer import anchor_target_layer_torch
+    from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
+    Hf, Wf, W, H, A, G = 24, 78, 1242, 375, 25, 12
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0])
+    gt = synth_gt(91, G, W, H)
+    gt[:3, 2:4] = gt[:3, :2] + 3.0                   # tiny boxes: their best anchors overlap < 0.3
+    info = np.array([0, W, 0, H, 0, 0, 1.0], dtype=np.float32)
+    outs = {}
+    for clobber in (False, True):
+        cfg.TRAIN.RPN_CLOBBER_POSITIVES = clobber
+        try:
+            torch.manual_seed(4)
+            want = O.anchor_target_layer(gt, torch.zeros(0, 5), info, anchors, A, Hf, Wf,
+                                         cfg=O.GlueCfg(rpn_clobber_positives=clobber))
+            torch.manual_seed(4)
+            got = anchor_target_layer_torch(gt.to(dev()), torch.zeros(0, 5, device=dev()), info, anchors.to(dev()), A,
+                                            Hf, Wf, torch.device("cpu"))
+        finally:
+            cfg.TRAIN.RPN_CLOBBER_POSITIVES = False
+        assert torch.equal(got[0].cpu(), want[0]), f"labels, clobber={clobber}"
+        close(got[1], want[1])
+        assert torch.equal(got[2].cpu(), want[2]) and torch.equal(got[3].cpu(), want[3])
+        outs[clobber] = int((want[0] == 1).sum())
+    assert outs[True] < outs[False]                  # the branch really changed the labelling
+
+
+@pytest.mark.parametrize("use_gt,ignore_dc", [(True, False), (False, True), (True, True)])
+def test_proposal_target_use_gt_and_ignore_dc_vs_oracle(golden, use_gt, ignore_dc):
+    """cfg.TRAIN.USE_GT (proposal_target_layer.py:35-41: GT boxes join the candidates) and cfg.TRAIN.IGNORE_DC
+    (:184-190: candidates overlapping a don't-care box by >= DC_THRESH are dropped before sampling)."""
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils import proposal_target_layer as ptl
+    from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
+    g = golden("proposal_target")
+    rois, scores, a3d = torch.from_numpy(g["rois"]), torch.from_numpy(g["scores"]), torch.from_numpy(g["a3d"])
+    gt, gt8 = torch.from_numpy(g["gt"]), torch.from_numpy(g["gt8"])
+    dc = torch.cat((rois[5:60:9, 1:5] + 2.0, torch.zeros(7, 1)), 1)          # don't-care boxes on top of some RoIs
+    cfg.NET_TYPE, cfg.TRAIN.BG_MODE, ptl.RNG_DEVICE = "image", "intended", "cpu"
+    cfg.TRAIN.USE_GT, cfg.TRAIN.IGNORE_DC = use_gt, ignore_dc
+    try:
+        torch.manual_seed(6)
+        got = ptl.proposal_target_layer(T(rois), T(scores), T(a3d), T(gt), T(gt8), T(dc), 4, 4)
+    finally:
+        cfg.NET_TYPE, cfg.TRAIN.BG_MODE, ptl.RNG_DEVICE = "lidar", "strict", None
+        cfg.TRAIN.USE_GT, cfg.TRAIN.IGNORE_DC = False, False
+    torch.manual_seed(6)
+    ocfg = O.GlueCfg(net_type="image", use_gt=use_gt, ignore_dc=ignore_dc)
+    want = O.proposal_target_layer(rois, scores, a3d, gt, gt8, dc, 4, 4, cfg=ocfg, bg_mode="intended")
+    for i, (a, b) in enumerate(zip(got, want)):
+        if i == 4:
+            close(a, b, atol=1e-5)
+        else:
+            assert torch.equal(a.cpu(), b), i
+    if ignore_dc:      # the dropped candidates never show up among the sampled RoIs
+        kept = want[1][:, 1:5]
+        assert float(O.bbox_overlaps(kept.contiguous(), dc[:, :4].contiguous()).max()) < ocfg.dc_thresh
+
+
 # ------------------------------------------------------------------------------------------
 # MC-dropout reductions
 # ------------------------------------------------------------------------------------------
@@ -712,12 +772,13 @@ def test_nms_hstack_torch_golden(golden):
         assert np.array_equal(inds.cpu().numpy(), g[f"k4_inds{c}"]) and np.array_equal(keep, g[f"k4_keep{c}"])
 
 
-@pytest.mark.parametrize("db_type,E", [("image", 4), ("lidar", 7)])
-def test_final_detections_batched(db_type, E):
+@pytest.mark.parametrize("db_type,E,R", [("image", 4, 300), ("lidar", 7, 300), ("image", 4, 2000), ("lidar", 7, 2500)])
+def test_final_detections_batched(db_type, E, R):
     """F frames x K classes in one launch vs the oracle per frame: ragged roi counts, max_dets with ties,
-    an empty class, uncertainty gathers."""
+    an empty class, uncertainty gathers.  R = 2000 is cfg.TRAIN.RPN_POST_NMS_TOP_N (the RoIs a train-mode frame
+    hands to filter_and_draw_prep); more than 1024 RoIs take the 1024-thread launch."""
     from faster_rcnn_pytorch_multimodal_b200 import ops
-    F, R, K, max_dets = 3, 300, 4, 20
+    F, K, max_dets = 3, 4, 20
     g = torch.Generator().manual_seed(77)
     probs = torch.softmax(torch.randn(F, R, K, generator=g) * 2.0, dim=2)
     probs[:, :, 3] = 0.01                                   # class 3 never passes the threshold
