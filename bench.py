@@ -502,6 +502,58 @@ def torchvision_cuda_baseline(h, cfg, prob, deltas, feat, info, anchors, a3d, it
             "frames_per_step": F, "what": what + " + torchvision.ops.roi_align (stock sm_100 kernels), median of CUDA-event timings"}
 
 
+def torchvision_cuda_train_baseline(cfg, prob, deltas, feat, info, anchors, a3d, gts, true_gt, dc, grad_out, K, ours_fps):
+    """Train-mode bar: the reference's proposal_layer (12000 -> 2000) + anchor_target_layer_torch +
+    proposal_target_layer on CUDA tensors, frame by frame as the reference runs them, then torchvision's
+    roi_align forward + backward (stock K2 / K3) on the sampled RoIs."""
+    try:
+        import torchvision
+        ref, src = load_reference()
+        if ref is None:
+            return {"unavailable": "reference functions not staged (oracle/_ref)"}
+        rc = ref.cfg
+        rc.TRAIN.RPN_PRE_NMS_TOP_N, rc.TRAIN.RPN_POST_NMS_TOP_N, rc.TRAIN.RPN_NMS_THRESH = \
+            cfg["pre_nms"], cfg["post_nms"], cfg["nms_thresh"]
+        rc.NET_TYPE = "image"
+        F, A, P = prob.shape[0], cfg["A"], cfg["pooled"]
+        dev = prob.device
+        info_np = info[0].cpu().numpy()
+        sc, sr = 1.0 / cfg["stride"], cfg["sampling_ratio"]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def one_step():
+            ev[0].record()
+            props = [ref.pl.proposal_layer(prob[f:f + 1], deltas[f:f + 1], info_np, "TRAIN", anchors, a3d, A) for f in range(F)]
+            ev[1].record()
+            sampled = []
+            for f in range(F):
+                ref.atl.anchor_target_layer_torch(gts[f], dc, info_np, anchors, A, cfg["Hf"], cfg["Wf"], dev)
+                out = ref.prt.proposal_target_layer(props[f][0], props[f][1], props[f][2], gts[f], true_gt, dc, K, 4)
+                r = out[1].clone()
+                r[:, 0] = f
+                sampled.append(r)
+            sampled = torch.cat(sampled)
+            ev[2].record()
+            fg = feat.detach().requires_grad_(True)
+            pooled = torchvision.ops.roi_align(fg, sampled, (P, P), sc, sr)
+            pooled.backward(grad_out[:sampled.shape[0]])
+            ev[3].record()
+            torch.cuda.synchronize()
+            return [a.elapsed_time(b) for a, b in zip(ev[:-1], ev[1:])]
+
+        one_step()
+        ts = np.median(np.array([one_step() for _ in range(3)]), axis=0)
+        total = float(ts.sum())
+        return {"value": F / (total * 1e-3), "unit": "frames/s", "frames_per_step": F,
+                "stage_ms_per_step": {"proposal": float(ts[0]), "targets": float(ts[1]), "roi_fwd_bwd": float(ts[2])},
+                "speedup_device_resident": ours_fps / (F / (total * 1e-3)),
+                "what": "unmodified reference proposal_layer / anchor_target_layer_torch / proposal_target_layer (" + src +
+                        ") on CUDA tensors, frame by frame, + torchvision.ops.roi_align forward and backward (stock sm_100 "
+                        "kernels); CUDA events, median of 3"}
+    except BaseException as e:       # the reference drops into pdb when a frame has no fg and no bg RoIs
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+
+
 def parity_gate_inference(cfg, ops, dev, prob, deltas, feat, info, anchors, a3d, rois, scores, num, pooled):
     """Frames 0 and F-1 of the timed batch against the oracle: selection order and keep list exact (NMS re-run on
     OUR decoded boxes by torchvision-CPU), decoded boxes 1e-3 abs, pooled features 1e-5 vs torchvision-CPU."""
@@ -679,6 +731,7 @@ def run_train(args, cfg):
     from faster_rcnn_pytorch_multimodal_b200 import ops
     from faster_rcnn_pytorch_multimodal_b200.layer_utils.anchor_target_layer import anchor_target_layer_torch
     from faster_rcnn_pytorch_multimodal_b200.layer_utils.proposal_target_layer import proposal_target_layer
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.batched_targets import train_targets_batched
     from faster_rcnn_pytorch_multimodal_b200.model.config import cfg as pcfg
     pcfg.NET_TYPE = "image"
     F = args.frames or cfg["frames"]
@@ -700,13 +753,12 @@ def run_train(args, cfg):
         rois, scores, a3k, _, num = ops.proposal_batched(prob, deltas, info, anchors, a3d, A, cfg["pre_nms"],
                                                          cfg["post_nms"], cfg["nms_thresh"], batch_index_stride=0)
         ev[1].record()
-        nn = num.tolist()                                    # the reference's own host sync (keep.numel())
+        # targets of all F frames: device phases back to back, ONE transfer of the samplers' counts, the draws in
+        # frame-by-frame order (layer_utils/batched_targets.py; equals the per-frame functions, tested)
+        tg = train_targets_batched(gts, info, anchors, A, cfg["Hf"], cfg["Wf"], rois, scores, a3k, num, None, K, 4)
         sampled = []
         for f in range(F):
-            anchor_target_layer_torch(gts[f], dc, info_np, anchors, A, cfg["Hf"], cfg["Wf"], dev)
-            out = proposal_target_layer(rois[f, :nn[f]], scores[f, :nn[f]].view(-1, 1), a3k[f, :nn[f]], gts[f], true_gt,
-                                        dc, K, 4)
-            r = out[1].clone()
+            r = tg[4][f][1].clone()
             r[:, 0] = f
             sampled.append(r)
         sampled = torch.cat(sampled)
@@ -775,8 +827,12 @@ def run_train(args, cfg):
                         "d2h_bytes_per_step": int(o_pool.nbytes + o_g.nbytes), "frames_per_call": 1,
                         "note": "public Python API, one frame per call, pinned host tensors in and out"},
                 "gpu_launches": launches, "clocks": clocks,
-                "note": "anchor / proposal targets run one frame per call with the reference's own host syncs "
-                        "(randperm sizes): the target stage is launch- and sync-bound, not bandwidth-bound"}
+                "note": "anchor / proposal targets of the F frames of a step share ONE host sync for the samplers' counts "
+                        "(the reference's randperm sizes are data dependent); the e2e leg runs the reference's one-frame "
+                        "API with its per-frame syncs"}
+        if not args.no_gpu_baseline:
+            line["gpu_baseline"] = torchvision_cuda_train_baseline(cfg, prob, deltas, feat, info, anchors, a3d, gts, true_gt,
+                                                                   dc, grad_out, K, value / world)
         add_cpu_baseline(line, args, cfg)
     h.finish(line)
 

@@ -698,6 +698,41 @@ def test_proposal_target_use_gt_and_ignore_dc_vs_oracle(golden, use_gt, ignore_d
         assert float(O.bbox_overlaps(kept.contiguous(), dc[:, :4].contiguous()).max()) < ocfg.dc_thresh
 
 
+def test_train_targets_batched_equals_frame_by_frame():
+    """Anchor + RoI targets of F frames with ONE host sync for the samplers' counts: the draws are made in the order
+    a frame-by-frame run makes them, so a seeded run returns exactly what the per-frame functions return."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils import proposal_target_layer as ptl
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.anchor_target_layer import anchor_target_layer_torch
+    from faster_rcnn_pytorch_multimodal_b200.layer_utils.batched_targets import train_targets_batched
+    from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
+    Hf, Wf, W, H, A, F, K = 24, 78, 1242, 375, 25, 3, 4
+    prob, deltas = synth_rpn(21, Hf, Wf, A, F=F)
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0]).to(dev())
+    info = torch.tensor([[0, W, 0, H, 0, 0, 1.0]]).repeat(F, 1).to(dev())
+    gts = [synth_gt(50 + f, g, W, H, K).to(dev()) for f, g in enumerate((12, 1, 30))]     # ragged GT counts
+    a3 = torch.arange(anchors.shape[0] * 7, dtype=torch.float32, device=dev()).view(-1, 7)
+    rois, sc, a3k, _, num = ops.proposal_batched(prob.to(dev()), deltas.to(dev()), info, anchors, a3, A, 12000, 2000, 0.7,
+                                                 batch_index_stride=0)
+    cfg.NET_TYPE, cfg.TRAIN.BG_MODE, ptl.RNG_DEVICE = "image", "intended", "cpu"
+    try:
+        torch.manual_seed(9)
+        got = train_targets_batched(gts, info, anchors, A, Hf, Wf, rois, sc, a3k, num, None, K, 4, dev="cpu")
+        torch.manual_seed(9)
+        nn = num.tolist()
+        for f in range(F):
+            at = anchor_target_layer_torch(gts[f], torch.zeros(0, 5, device=dev()), info[f].cpu().numpy(), anchors, A, Hf, Wf,
+                                           torch.device("cpu"))
+            pt = ptl.proposal_target_layer(rois[f, :nn[f]], sc[f, :nn[f]].view(-1, 1), a3k[f, :nn[f]], gts[f], None,
+                                           torch.zeros(0, 5, device=dev()), K, 4)
+            for i in range(4):
+                assert torch.equal(got[i][f], at[i][0]), ("anchor targets", f, i)
+            for i in range(7):
+                assert torch.equal(got[4][f][i], pt[i]), ("roi targets", f, i)
+    finally:
+        cfg.NET_TYPE, cfg.TRAIN.BG_MODE, ptl.RNG_DEVICE = "lidar", "strict", None
+
+
 # ------------------------------------------------------------------------------------------
 # MC-dropout reductions
 # ------------------------------------------------------------------------------------------
