@@ -57,6 +57,8 @@ PROTOTYPES = {
     "b2d_mc_variance": (I, [I, I, _f, I, _f, _v]),
     "b2d_mc_class_uncertainty": (I, [I, I, I, _f, _f, _f, _v]),
     "b2d_var_sort": (I, [I, I, _f, I, _f, _i, _v]),
+    "b2d_bbox_voxel_grid_to_pc": (I, [I, I, F32, F32, F32, F32, I, _f, _v]),
+    "b2d_eval_match": (I, [I, I, I, I, _f, _i, _i, _i, _f, _i, _i, _f, F64, F64, I, _i, _f, _i, _i, _v, _v]),
     "b2d_head_tail_decode": (I, [I, I, I, I, I, _f, _f, _f, _f, _f, _f, C.POINTER(C.c_float), C.POINTER(C.c_float), I, I, I,
                                  _f, _f, _f, _f, _f, _f, _v]),
     "b2d_bev_workspace_bytes": (SZ, [I, I, I, I]),

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2dglue.so")
 OBJ_DIR = os.path.join(CSRC, "_build")
 SOURCES = ["lib.cu", "proposal.cu", "nms.cu", "roi_align.cu", "roi_align_rows.cu", "roi_align_bwd_rows.cu",
-           "codecs.cu", "targets.cu", "uncertainty.cu", "detections.cu", "bev.cu", "head_tail.cu"]
+           "codecs.cu", "targets.cu", "uncertainty.cu", "detections.cu", "bev.cu", "head_tail.cu", "eval.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"]
 CC_FLAGS = ARCH_FLAGS + ["-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 LINK_FLAGS = ["--shared", "-cudart", "shared"] + ARCH_FLAGS

@@ -70,6 +70,7 @@ __C.TEST.RPN_PRE_NMS_TOP_N = 6000            # config.py:253
 __C.TEST.RPN_POST_NMS_TOP_N = 300            # config.py:256
 __C.TEST.MODE = 'nms'                        # config.py:263
 __C.TEST.RPN_TOP_N = 5000                    # config.py:266
+__C.TEST.IGNORE_DC = False                   # config.py:268
 
 __C.UC = AttrDict()
 __C.UC.EN_BBOX_ALEATORIC = False             # config.py:39

@@ -359,6 +359,36 @@ int b2d_proposal_crop_host(int num_frames, int n_loc, int num_anchors, int chann
                            float* rois_host, float* scores_host, int32_t* num_out_host, float* pooled_host,
                            void* device_ws, size_t device_ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Result post-processing and evaluation.
+ *
+ * b2d_bbox_voxel_grid_to_pc: utils/bbox.py:140-162, applied by model/test.py:224 to a lidar frame's detections
+ *   before they are stacked into all_boxes.  boxes [n, row_stride] fp32, transformed in place:
+ *   x = x*fx + x0, y = y*fy + y0, then (aabb) x2, y2 likewise or (7-DoF) l *= fx, w *= fy.  The caller computes
+ *   fx = (ext[3]-ext[0])/(s_info[1]-s_info[0]), fy = (ext[4]-ext[1])/(s_info[3]-s_info[2]), x0 = ext[0], y0 = ext[1]
+ *   in fp32 with s_info = info[0:6]/info[6].
+ *
+ * b2d_eval_match: the confidence-ordered greedy matching loop of datasets/waymo_eval.py:120-215 (kitti_eval.py and
+ *   cadc_eval.py share it).  Detections of one class in DESCENDING confidence order, float64 as the reference
+ *   parses them from the result file; frames ("recs") are independent:
+ *     det_boxes [n_det, box_elem]; rec_det_offset [n_rec+1] + rec_det_index: for every frame the positions of its
+ *     detections in that order (ascending); gt_offset [n_rec+1], gt_boxes [sum G, box_elem], gt_flags [sum G]
+ *     (bit 0: ignore, bits 8..: difficulty); dc_offset [n_rec+1], dc_boxes [sum D, box_elem] (don't-care boxes,
+ *     used when ignore_dc != 0, cfg.TEST.IGNORE_DC).  mode 0 = '2d' boxes [x1,y1,x2,y2] (+1 pixel convention),
+ *     mode 1 = 'bev_aa' axis-aligned footprint of [xc,yc,zc,l,w,h,ry].
+ *   Outputs per detection: code (0 nothing recorded, 1 true positive, 2 false positive on an already matched box,
+ *   3 false positive below the overlap threshold; detections of frames that are not evaluated are simply not
+ *   listed and keep whatever the caller initialised), ovmax (fp64, -inf without ground truth), jmax (first argmax),
+ *   difficulty of the matched box (-1 unless code 1 or 2).  hit_scratch: sum G bytes.
+ * ---------------------------------------------------------------------------------- */
+int b2d_bbox_voxel_grid_to_pc(int n, int row_stride, float fx, float fy, float x0, float y0, int aabb, float* boxes,
+                              void* stream);
+int b2d_eval_match(int n_det, int n_rec, int box_elem, int mode, const double* det_boxes,
+                   const int32_t* rec_det_offset, const int32_t* rec_det_index, const int32_t* gt_offset,
+                   const double* gt_boxes, const int32_t* gt_flags, const int32_t* dc_offset, const double* dc_boxes,
+                   double ovthresh, double ovthresh_dc, int ignore_dc, int32_t* code, double* ovmax, int32_t* jmax,
+                   int32_t* difficulty, unsigned char* hit_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -399,7 +399,160 @@ def gen_head_tail():
     print("head_tail.npz", os.path.getsize(os.path.join(OUT, "head_tail.npz")))
 
 
+def gen_eval():
+    """tests/golden/eval.npz: result files + detection matching from the reference's own
+    writers and its own waymo_eval loop, run with the missing utils/eval_utils.py bound to oracle/eval_oracle.py."""
+    import json
+    import tempfile
+    import types
+    from . import eval_oracle as E
+    ns = ref_import.load_eval()
+    cfg = ns.cfg
+    rng = np.random.RandomState(SEED)
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="b2d_eval_")
+    cfg.ROOT_DIR = tmp                                   # get_output_dir() builds its path under cfg.ROOT_DIR
+    classes = ('__background__', 'vehicle', 'pedestrian')
+    tokens = ['%07d.png' % (1000 * s + i) for s, i in ((0, 3), (0, 4), (1, 0), (1, 7), (2, 5), (2, 6))]
+    F, K, U = len(tokens), len(classes), 3
+
+    for nt, E_, eval_type in (("image", 4, "2d"), ("lidar", 7, "bev_aa")):
+        cfg.NET_TYPE = nt
+        # ---- ground truth: frame 3 is absent from the label file, frame 4 has no boxes at all
+        labels, recs_in = [], {}
+        for f, tok in enumerate(tokens):
+            if f == 3:
+                continue
+            G = 0 if f == 4 else 5 + f
+            if nt == "image":
+                xy = rng.rand(G, 2) * np.array([1500.0, 900.0])
+                wh = rng.rand(G, 2) * 200 + 30
+                boxes = np.concatenate((xy, xy + wh), 1)
+                dcxy = rng.rand(2, 2) * np.array([1500.0, 900.0])
+                boxes_dc = np.concatenate((dcxy, dcxy + 150), 1)
+            else:
+                boxes = np.concatenate((rng.rand(G, 2) * 60 - 30, rng.rand(G, 1), rng.rand(G, 3) * np.array([4.0, 2.0, 1.0]) + 1.5,
+                                        rng.rand(G, 1) * 3 - 1.5), 1)
+                boxes_dc = np.concatenate((rng.rand(2, 2) * 60 - 30, np.zeros((2, 1)), np.full((2, 3), 6.0), np.zeros((2, 1))), 1)
+            rec = dict(boxes=boxes.astype(np.float32), boxes_dc=boxes_dc.astype(np.float32),
+                       gt_classes=rng.randint(1, K, G), difficulty=rng.randint(0, 4, G), ignore=rng.rand(G) < 0.2,
+                       pts=rng.randint(5, 500, G), ids=['trk%d_%d' % (f, j) for j in range(G)], scene_idx=f // 2,
+                       scene_desc='scene%d' % (f // 2))
+            recs_in[tok] = rec
+            labels.append({'assoc_frame': str(int(''.join(c for c in tok if c.isdigit()))).zfill(7), 'token': tok})
+
+        class FakeDb(object):
+            name = 'waymo_fake'
+            _devkit_path = tmp
+            _class_to_ind = dict(zip(classes, range(K)))
+
+            def __init__(self):
+                self.classes = classes
+
+            def _get_index_for_mode(self, mode):
+                return tokens
+            _get_results_file_template = ns.db.db._get_results_file_template
+
+            def _load_waymo_annotation(self, frame, label, remove_without_gt=False, tod_filter_list=None, en_aux_features=False):
+                r = recs_in[label['token']]
+                G = len(r['gt_classes'])
+                return dict(boxes=r['boxes'].copy(), boxes_dc=r['boxes_dc'].copy(), gt_classes=r['gt_classes'].copy(),
+                            gt_overlaps=np.zeros((G, K)), det=np.zeros(G, dtype=bool), ignore=r['ignore'].copy(),
+                            hit=np.zeros(G, dtype=bool), ids=list(r['ids']), pts=r['pts'].copy(),
+                            difficulty=r['difficulty'].copy(), scene_idx=r['scene_idx'], scene_desc=r['scene_desc'])
+        db = FakeDb()
+        os.makedirs(os.path.join(tmp, 'test', 'labels'), exist_ok=True)
+        with open(os.path.join(tmp, 'test', 'labels', E.get_labels_filename(db, eval_type)), 'w') as fh:
+            json.dump(labels, fh)
+        # ---- detections: jittered GT (some twice), clutter, detections in frames that are not evaluated
+        all_boxes = [[np.empty(0) for _ in range(F)] for _ in range(K)]
+        for f, tok in enumerate(tokens):
+            for c in range(1, K):
+                rows = []
+                r = recs_in.get(tok)
+                if r is not None:
+                    for j in np.where(r['gt_classes'] == c)[0]:
+                        for rep in range(1 + (j % 3 == 0)):
+                            b = r['boxes'][j].astype(np.float64) + rng.randn(E_) * (4.0 if nt == "image" else 0.15) * (1 + rep)
+                            rows.append(np.concatenate((b, [rng.rand() * 0.9 + 0.1], rng.rand(U))))
+                    for j in range(2):                                   # on top of the don't-care boxes
+                        b = r['boxes_dc'][j].astype(np.float64) + rng.randn(E_) * 0.5
+                        rows.append(np.concatenate((b, [rng.rand()], rng.rand(U))))
+                for _ in range(3):                                       # clutter
+                    if nt == "image":
+                        xy = rng.rand(2) * np.array([1500.0, 900.0])
+                        b = np.concatenate((xy, xy + rng.rand(2) * 100 + 20))
+                    else:
+                        b = np.concatenate((rng.rand(2) * 60 - 30, [0.5], rng.rand(3) * 3 + 1, [0.0]))
+                    rows.append(np.concatenate((b, [rng.rand() * 0.5], rng.rand(U))))
+                if f == 5 and c == 2:
+                    rows = []                                            # a class without detections in a frame
+                if rows:
+                    all_boxes[c][f] = np.stack(rows).astype(np.float32)
+        # confidences unique at the three decimals the result file keeps: the reference orders equal confidences
+        # with numpy's unstable argsort (waymo_eval.py:129), which no fixture should depend on
+        for c in range(1, K):
+            total = sum(a.shape[0] for a in all_boxes[c] if a.size)
+            uniq = (rng.permutation(998)[:total] + 1) / 1000.0
+            p0 = 0
+            for f in range(F):
+                if all_boxes[c][f].size:
+                    m = all_boxes[c][f].shape[0]
+                    all_boxes[c][f][:, E_] = uniq[p0:p0 + m]
+                    p0 += m
+        out_dir = os.path.join(tmp, nt)
+        os.makedirs(out_dir, exist_ok=True)
+        writer = ns.db.db._write_image_results_file if nt == "image" else ns.db.db._write_lidar_results_file
+        writer(db, all_boxes, out_dir, 'test')
+        for c in range(1, K):
+            path = db._get_results_file_template('test', classes[c], out_dir)
+            with open(path) as fh:
+                out[f"{nt}_lines_{c}"] = np.array(fh.readlines())
+        for c in range(1, K):
+            for f in range(F):
+                out[f"{nt}_dets_{c}_{f}"] = all_boxes[c][f]
+        for tok, r in recs_in.items():
+            f = tokens.index(tok)
+            for k in ('boxes', 'boxes_dc', 'gt_classes', 'difficulty', 'ignore', 'pts'):
+                out[f"{nt}_gt_{f}_{k}"] = np.asarray(r[k])
+        # ---- the reference's evaluation loop
+        detpath = os.path.join(out_dir, 'results', 'det_test_{:s}.txt')
+        for ign_dc in (False, True):
+            cfg.TEST.IGNORE_DC = ign_dc
+            for c in range(1, K):
+                E.SAVED.clear()
+                mrec, mprec, mp = ns.waymo_eval.waymo_eval(detpath, db, tokens, classes[c], None, 'test', ovthresh=0.5,
+                                                           eval_type=eval_type, d_levels=2)
+                tag = f"{nt}_eval_{c}_{int(ign_dc)}"
+                out[tag + "_map"] = np.asarray(mp, dtype=np.float64)
+                out[tag + "_mrec"] = np.asarray(mrec, dtype=np.float64)
+                out[tag + "_mprec"] = np.asarray(mprec, dtype=np.float64)
+                out[tag + "_results"] = np.array(E.SAVED['{}_detection_results.txt'.format(classes[c])])
+        cfg.TEST.IGNORE_DC = False
+    out["tokens"] = np.array(tokens)
+    out["classes"] = np.array(classes)
+    # ---- stack_uncertainties (model/test.py:260-270) and bbox_voxel_grid_to_pc (utils/bbox.py:140-162)
+    cls_boxes = (rng.rand(9, 8) * 50).astype(np.float32)
+    ucs = {'a_bbox_var': rng.rand(9, 7).astype(np.float32), 'e_bbox_var': rng.rand(9, 7).astype(np.float32),
+           'a_entropy': rng.rand(9, 1).astype(np.float32), 'e_mutual_info': rng.rand(9, 1).astype(np.float32)}
+    out["stack_boxes"], out["stack_hstack"] = cls_boxes, ns.test.stack_uncertainties(cls_boxes, ucs, 16)
+    for k, v in ucs.items():
+        out["stack_uc_" + k] = v
+    extents = [0.0, -40.0, 0.0, 70.0, 40.0, 3.0]
+    info = np.array([0, 700, 0, 800, 0, 12, 1.0], dtype=np.float32)
+    info2 = np.array([0, 1400, 0, 1600, 0, 24, 2.0], dtype=np.float32)
+    vg = (rng.rand(11, 8) * 300).astype(np.float32)
+    out["vg_in"], out["vg_extents"], out["vg_info"], out["vg_info2"] = vg, np.array(extents), info, info2
+    out["vg_out"] = ns.ub.bbox_voxel_grid_to_pc(vg.copy(), extents, info)
+    out["vg_out2"] = ns.ub.bbox_voxel_grid_to_pc(vg.copy(), extents, info2)
+    out["vg_out_aabb"] = ns.ub.bbox_voxel_grid_to_pc(vg[:, :4].copy(), extents, info, aabb=True)
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **out)
+    print("eval.npz", os.path.getsize(os.path.join(OUT, "eval.npz")))
+
+
 if __name__ == "__main__":
+    if "--only-eval" in sys.argv:
+        sys.exit(gen_eval())
     if "--only-bev" in sys.argv:
         sys.exit(gen_bev())
     if "--only-head-tail" in sys.argv:
@@ -407,4 +560,5 @@ if __name__ == "__main__":
     rc = main()
     gen_bev()
     gen_head_tail()
+    gen_eval()
     sys.exit(rc)

@@ -134,3 +134,51 @@ def load_minibatch():
     sp.utils = stub("spconv.utils", VoxelGeneratorV2=bev_oracle.VoxelGeneratorV2)
     import roi_data_layer.minibatch as mb
     return mb
+
+
+def load_eval():
+    """Import the reference's result writers and evaluation loop: ``datasets/db.py``
+    (`_write_image_results_file`, `_write_lidar_results_file`), ``model/test.py`` (`stack_uncertainties`),
+    ``utils/bbox.py`` (`bbox_voxel_grid_to_pc`) and ``datasets/waymo_eval.py`` (`waymo_eval`).
+
+    ``utils/eval_utils.py`` is MISSING from the reference snapshot: it is bound to the restatement in
+    ``oracle/eval_oracle.py`` - those eight helpers are the parity-unpinned part of this row.  Everything else the
+    modules import and this path never touches (plotting, augmentation, point-cloud IO, shapely, the dataset
+    classes' own dependencies) is stubbed with empty modules."""
+    if not os.path.isdir("/root/reference/lib/datasets"):
+        raise RuntimeError("/root/reference is not present (the evaluation modules are not staged for the GPU box)")
+    ns = load()
+    from . import eval_oracle
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return object
+
+    sys.modules["utils.eval_utils"] = eval_oracle
+    import utils
+    utils.eval_utils = eval_oracle
+    mods = {}
+    for target in ("datasets.db", "datasets.waymo_eval", "model.test"):
+        for _ in range(40):
+            try:
+                mods[target] = __import__(target, fromlist=["x"])
+                break
+            except ModuleNotFoundError as e:
+                name = e.name
+                if name.startswith(("datasets", "model", "layer_utils", "nets", "roi_data_layer")) or name in (
+                        "utils.bbox", "utils.filter_predictions", "utils.blob", "utils.timer"):
+                    raise
+                parts = name.split(".")
+                for i in range(1, len(parts) + 1):
+                    n = ".".join(parts[:i])
+                    if n not in sys.modules:
+                        sys.modules[n] = _Any(n)
+                        sys.modules[n].__path__ = []
+                    if i > 1:
+                        setattr(sys.modules[".".join(parts[:i - 1])], parts[i - 1], sys.modules[n])
+        else:
+            raise RuntimeError("could not import " + target)
+    ns.db, ns.waymo_eval, ns.test = mods["datasets.db"], mods["datasets.waymo_eval"], mods["model.test"]
+    return ns
