@@ -111,7 +111,12 @@ constexpr int kMaxBlk = 64;        // ring blocks (mbarrier pairs)
 constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): each streams one band of rows
 constexpr int kRowBlkShift = 18;   // row entries: ring byte offset (< 227 KB) in the low bits, block of the row above
 
-constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps
+constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps (minimum)
+constexpr int kMaxPool = 8;                 // ... and as many as fit once the ring has kPoolRingRows rows (chosen by the plan)
+constexpr int kPoolRingRows = 12;
+// per consumer warp: its record slot (512 B), overlaid by its bin-row output tile [32 ch][7] (896 B) - the record is
+// dead once the row loop of an item has finished
+constexpr int kWarpAreaBytes = kCh * kP * 4 > kRecBytes ? kCh * kP * 4 : kRecBytes;
 constexpr int kTileWords = kCh * kP * kP;
 constexpr int kStages = B2D_STAGES;         // staging rows of the TMA fill
 constexpr int kProducers = 2;               // producer warps of the TMA fill (each repacks 32 / kProducers channels)
@@ -120,7 +125,7 @@ struct Plan {
   int fill;         // 0: cooperative cp.async; 1: TMA + repack producer warp
   int lane_stride;  // words between channels of one slot (odd)
   int row_words;    // words per ring slot
-  int Rr, St, nblk, nbk, span_max, span_whole, nsteps;
+  int Rr, St, nblk, nbk, span_max, span_whole, nsteps, npool;
   size_t smem;
   bool ok;
 };
@@ -139,9 +144,23 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   const size_t row_bytes = (size_t)p.row_words * 4;
   const size_t staging = p.fill ? (size_t)kStages * kCh * stage_width(W) * 4 : 0;
   const int nslot = p.fill ? kWarps - kProducers : kWarps;      // consumer warps own a record slot and a bin-row tile
-  const size_t pool = p.fill ? (size_t)kPool * kTileWords * 4 : 0;
-  const size_t fixed = (size_t)nslot * kRecBytes + (size_t)nslot * kCh * kP * 4 + 256 + staging + pool;
+  const size_t tile_bytes = (size_t)kTileWords * 4;
   const size_t budget = 227 * 1024 - 1280;       // 1.2 KB of static shared memory (barriers, locks, counters)
+  // Pool tiles: every whole-RoI item that finds no free tile falls back to the scattered bin-row stores, so small
+  // maps, whose ring does not need all of shared memory, get up to kMaxPool tiles (KITTI 24x78: -7 %, BEV 50x44:
+  // -13 % with 6-8 tiles); a tile is only added while the ring keeps kPoolRingRows rows (or the whole map) -
+  // on the 80x120 Waymo map a third tile costs a ring row and loses.
+  p.npool = p.fill ? kPool : 0;
+  auto fixed_for = [&](int npool) { return (size_t)nslot * kWarpAreaBytes + 256 + staging + (size_t)npool * tile_bytes; };
+  while (p.fill && p.npool < kMaxPool) {
+    const size_t f0 = fixed_for(p.npool), f1 = fixed_for(p.npool + 1);
+    if (f1 + 6 * row_bytes > budget) break;
+    const int rows0 = (int)((budget - f0) / row_bytes), rows1 = (int)((budget - f1) / row_bytes);
+    // free (fits in the remainder below a whole ring row) or affordable
+    if (rows1 < rows0 && rows1 < (H < kPoolRingRows ? H : kPoolRingRows)) break;
+    ++p.npool;
+  }
+  const size_t fixed = fixed_for(p.npool);
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
   if (Rr >= H) {
@@ -533,13 +552,13 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // of each lane go to shared memory once and leave with ONE bulk store of 6272 contiguous bytes; the tile stays
 // locked until the copy has read it (released at the warp's next item).  Without one the item takes the
 // bin-row path.
-__device__ __forceinline__ int tile_try_acquire(int* locks, int warp, int lane) {
+__device__ __forceinline__ int tile_try_acquire(int* locks, int npool, int warp, int lane) {
   unsigned t = 0;                          // tile index + 1, 0 = none
   if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kPool; ++k) {
-      const int i = (warp + k) % kPool;
-      if (t == 0 && atomicCAS(&locks[i], 0, 1) == 0) t = (unsigned)i + 1u;
+    int i = warp % npool;
+    for (int k = 0; k < npool && t == 0; ++k) {
+      if (atomicCAS(&locks[i], 0, 1) == 0) t = (unsigned)i + 1u;
+      if (++i == npool) i = 0;
     }
   }
   return (int)__reduce_max_sync(0xffffffffu, t) - 1;
@@ -565,7 +584,7 @@ template <int NPH, int S, bool POOL, class Landed>
 __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __restrict__ slot, int nrows, int nph, uint32_t lane_base,
                                          float* __restrict__ stage, int lane, float* __restrict__ o,
                                          const int (&ooff)[kP], unsigned omask,
-                                         float* __restrict__ pool, int* locks, int warp, bool tile_out, int& held) {
+                                         float* __restrict__ pool, int* locks, int npool, int warp, bool tile_out, int& held) {
   constexpr int NX = kP * S;
   constexpr int RV = NPH > 2 ? 2 : 1;
   constexpr bool PACK = S == 2;
@@ -705,8 +724,8 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
   return;      // A/B timing build: results discarded
 #endif
   if (POOL) {
-    if (NPH == kP && kPool > 0 && tile_out && nph == kP) {
-      const int t = tile_try_acquire(locks, warp, lane);
+    if (NPH == kP && tile_out && nph == kP) {
+      const int t = tile_try_acquire(locks, npool, warp, lane);
       if (t >= 0) {
         float* tile = pool + (size_t)t * kTileWords;
 #pragma unroll
@@ -742,7 +761,7 @@ struct KArgs {
   RoiList L;
   int C, H, W;
   int lane_stride, row_words, stage_w;
-  int St, nblk, nbk, items_cap, band_rows, halo;
+  int St, nblk, nbk, items_cap, band_rows, halo, npool;
   Ws ws;
   float* out;
 };
@@ -756,7 +775,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   __shared__ __align__(8) uint64_t done_bar[kMaxBlk];   // every consumer warp is past bucket j
   __shared__ __align__(8) uint64_t stg_bar[kStages];    // staging row landed (TMA bytes)
   __shared__ int s_ctr;
-  __shared__ int s_tile_lock[kPool > 0 ? kPool : 1];
+  __shared__ int s_tile_lock[kMaxPool];
   __shared__ int s_progress[kWarps];                    // TMA fill: bucket each consumer warp is working in
   constexpr int kConsumers = FILL ? kWarps - kProducers : kWarps;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -782,13 +801,13 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   // (pointer arithmetic on `smem` keeps the shared address space; a cast through an integer would
   // turn every slot / staging access into a generic load)
   float* ring = smem + (((128u - (smem_u32(smem) & 127u)) & 127u) >> 2);
-  float4* slot = reinterpret_cast<float4*>(ring + (size_t)St * nblk * row_words) + (size_t)warp * kRecVec;
-  float* stage = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)warp * kCh * kP;
-  float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * kRecBytes / 4 + (size_t)kConsumers * kCh * kP;
-  float* stg = pool + (FILL ? (size_t)kPool * kTileWords : 0);
+  float* stage = ring + (size_t)St * nblk * row_words + (size_t)warp * (kWarpAreaBytes / 4);
+  float4* slot = reinterpret_cast<float4*>(stage);
+  float* pool = ring + (size_t)St * nblk * row_words + (size_t)kConsumers * (kWarpAreaBytes / 4);
+  float* stg = pool + (FILL ? (size_t)a.npool * kTileWords : 0);
   const uint32_t ring_s = smem_u32(ring);
   if (tid < kWarps) s_progress[tid] = 0;
-  if (tid < kPool) s_tile_lock[tid] = 0;
+  if (tid < kMaxPool) s_tile_lock[tid] = 0;
   if (tid == 0) {
     s_ctr = 0;
     for (int i = 0; i < kStages; ++i) mbar_init(&stg_bar[i], 1);
@@ -845,28 +864,42 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
                            (uint32_t)(pw_id * kChP) * sstep;
       const uint32_t dst = ring_s + (uint32_t)((babs % nblk) * St + dy) * (uint32_t)(row_words * 4) + (uint32_t)lane * 4u +
                            (uint32_t)(pw_id * kChP) * dstep;
-      // batches of 8 channels x up to 4 chunks (32 values per lane)
+      // batches of 8 channels x up to 4 chunks (32 values per lane).  One address register per channel, the chunk
+      // offset as an immediate, the chunk predicates once per batch: the address arithmetic of a per-element
+      // formulation was two thirds of the repack's instructions.
       const int ncg = (nchunk + 3) / 4, nbat = (kChP / 8) * ncg;
+#define B2D_LD4(J, SJ)                                                                                         \
+  if (p0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[(J) * 4 + 0]) : "r"(SJ) : "memory");                 \
+  if (p1) asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(v[(J) * 4 + 1]) : "r"(SJ) : "memory");             \
+  if (p2) asm volatile("ld.shared.f32 %0, [%1+256];" : "=f"(v[(J) * 4 + 2]) : "r"(SJ) : "memory");             \
+  if (p3) asm volatile("ld.shared.f32 %0, [%1+384];" : "=f"(v[(J) * 4 + 3]) : "r"(SJ) : "memory");
+#define B2D_ST4(J, DJ)                                                                                         \
+  if (p0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 0]) : "memory");                   \
+  if (p1) asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 1]) : "memory");               \
+  if (p2) asm volatile("st.shared.f32 [%0+256], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 2]) : "memory");               \
+  if (p3) asm volatile("st.shared.f32 [%0+384], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 3]) : "memory");
       for (int bi = 0; bi < nbat; ++bi) {
         const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
+        const bool p0 = cg + 0 < nchunk - 1 || (cg + 0 == nchunk - 1 && tail_ok);
+        const bool p1 = cg + 1 < nchunk - 1 || (cg + 1 == nchunk - 1 && tail_ok);
+        const bool p2 = cg + 2 < nchunk - 1 || (cg + 2 == nchunk - 1 && tail_ok);
+        const bool p3 = cg + 3 < nchunk - 1 || (cg + 3 == nchunk - 1 && tail_ok);
         float v[32];
+        uint32_t sj = src + (uint32_t)c8 * sstep + 128u * (uint32_t)cg;
+        uint32_t dj = dst + (uint32_t)c8 * dstep + 128u * (uint32_t)cg;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j) {
+          B2D_LD4(j, sj)
+          sj += sstep;
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = cg + k;
-            if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j * 4 + k]) : "r"(src + (c8 + j) * sstep + 128u * ch) : "memory");
-          }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = cg + k;
-            if (ch < nchunk - 1 || (ch == nchunk - 1 && tail_ok))
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (c8 + j) * dstep + 128u * ch), "f"(v[j * 4 + k]) : "memory");
-          }
+        for (int j = 0; j < 8; ++j) {
+          B2D_ST4(j, dj)
+          dj += dstep;
+        }
       }
+#undef B2D_LD4
+#undef B2D_ST4
       __syncwarp();
       if (kProducers > 1) asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");   // all producers done with the buffer
       if (y + kStages < y_end) fetch(y + kStages);     // this staging buffer is free again
@@ -999,7 +1032,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   auto between_items = [&]() {
     // (`held` is warp-uniform; the reduction tells ptxas so - a branch it takes for divergent costs the
     // consumers their [column + uniform row] tap addressing)
-    if (FILL && kPool > 0 && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
+    if (FILL && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
       // the bulk store issued by the previous item has (nearly always) read its tile by now
       if (lane == 0) bulk_wait_read();
       tile_release(s_tile_lock, held, lane);
@@ -1053,7 +1086,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       // (only the blocks the item reads have to be there, not its whole window)
       release(bucket);
       if (!FILL) observe(min(last_blk + 1, nsteps));
-#define B2D_RUN(N) run_item<N, S, FILL>(wait_row, slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, warp, tile_out, held)
+#define B2D_RUN(N) run_item<N, S, FILL>(wait_row, slot, nrows, nph, lane_base, stage, lane, o, ooff, omask, pool, s_tile_lock, a.npool, warp, tile_out, held)
       if (nph <= 2) B2D_RUN(2);
       else if (nph <= 4) B2D_RUN(4);
       else B2D_RUN(7);
@@ -1157,7 +1190,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   // split > 1 (few frames): each of the `split` CTAs of a (frame, channel group) streams only its band of rows
   const int band_rows = ceil_div(ceil_div(H, split), p.St) * p.St;
   const int halo = (p.span_whole > p.span_max ? p.span_whole : p.span_max) - 1;
-  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, items_cap, band_rows, halo, ws, out};
+  KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, items_cap, band_rows, halo, p.npool, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
     prep_kernel<SS><<<dim3(ceil_div(per_frame, kPrepWarps), F), kPrepThreads,                                        \
