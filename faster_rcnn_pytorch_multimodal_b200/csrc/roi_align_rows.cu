@@ -112,7 +112,8 @@ constexpr int kMaxSplit = 4;       // CTAs sharing one (frame, channel group): e
 constexpr int kRowBlkShift = 18;   // row entries: ring byte offset (< 227 KB) in the low bits, block of the row above
 
 constexpr int kPool = B2D_POOL;             // TMA fill: output tiles [32 ch][49] shared by the consumer warps (minimum)
-constexpr int kMaxPool = 8;                 // ... and as many as fit once the ring has kPoolRingRows rows (chosen by the plan)
+constexpr int kMaxPool = 10;                // ... and as many as fit once the ring has kPoolRingRows rows (chosen by the plan);
+                                            // one per consumer warp = private tiles: no locks, no wait after the store
 constexpr int kPoolRingRows = 12;
 // per consumer warp: its record slot (512 B), overlaid by its bin-row output tile [32 ch][7] (896 B) - the record is
 // dead once the row loop of an item has finished
@@ -725,7 +726,19 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
 #endif
   if (POOL) {
     if (NPH == kP && tile_out && nph == kP) {
-      const int t = tile_try_acquire(locks, npool, warp, lane);
+      // npool tiles for the 10 consumer warps.  With a tile per warp (small maps) the tile is private: no lock, and
+      // the warp waits for its previous bulk store only here, an item later, when the copy has long read the tile.
+      const bool priv = npool >= kWarps - kProducers;
+      int t;
+      if (priv) {
+        t = warp;
+        if (__reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
+          if (lane == 0) bulk_wait_read();
+          __syncwarp();
+        }
+      } else {
+        t = tile_try_acquire(locks, npool, warp, lane);
+      }
       if (t >= 0) {
         float* tile = pool + (size_t)t * kTileWords;
 #pragma unroll
@@ -1032,7 +1045,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   auto between_items = [&]() {
     // (`held` is warp-uniform; the reduction tells ptxas so - a branch it takes for divergent costs the
     // consumers their [column + uniform row] tap addressing)
-    if (FILL && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
+    if (FILL && a.npool < kConsumers && __reduce_max_sync(0xffffffffu, (unsigned)(held + 1)) != 0u) {
       // the bulk store issued by the previous item has (nearly always) read its tile by now
       if (lane == 0) bulk_wait_read();
       tile_release(s_tile_lock, held, lane);
@@ -1121,6 +1134,10 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   // out of items: release every remaining bucket so the fill can finish
   release(nsteps);
   between_items();      // the last bulk store still reads shared memory
+  if (FILL && a.npool >= kConsumers && held >= 0) {
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+  }
   if (!FILL) {
     while (issued < nsteps) pump();
     asm volatile("cp.async.wait_all;" ::: "memory");
