@@ -91,6 +91,9 @@ namespace rows {
 #ifndef B2D_WARPS
 #define B2D_WARPS 12
 #endif
+#ifndef B2D_L2_AHEAD
+#define B2D_L2_AHEAD 2
+#endif
 #ifndef B2D_POLL_NS
 #define B2D_POLL_NS 64
 #endif
@@ -855,8 +858,16 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
         uint64_t* bar = &stg_bar[sb];
         mbar_expect_tx(bar, row_tx);
         tma_load_2d(smem_u32(stg + (size_t)sb * kCh * Ws), &tmap, (y * W) & ~3, plane0, bar);
+        if (B2D_L2_AHEAD > 0 && y + B2D_L2_AHEAD < y_end)      // pull a later row into L2: its TMA then pays L2 latency only
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap),
+                       "r"(((y + B2D_L2_AHEAD) * W) & ~3), "r"(plane0)
+                       : "memory");
       }
     };
+    if (B2D_L2_AHEAD > 0 && pw_id == 0 && lane == 0)
+      for (int y = y_begin + kStages; y < y_begin + kStages + B2D_L2_AHEAD && y < y_end; ++y)
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap), "r"((y * W) & ~3), "r"(plane0)
+                     : "memory");
     for (int y = y_begin; y < y_begin + kStages && y < y_end; ++y) fetch(y);
     for (int y = y_begin; y < y_end; ++y) {
       const int babs = y / St, dy = y - babs * St;
