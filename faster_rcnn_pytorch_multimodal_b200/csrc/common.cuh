@@ -75,6 +75,33 @@ inline float float_floor_of(double thr) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the kernel
+// before it in the stream is still running; it must call pdl_wait() before it touches anything an earlier kernel
+// wrote (a no-op in a normal launch).  pdl_trigger() lets the NEXT kernel's CTAs become resident early.  Used on the
+// few-frame paths, where a call is a chain of ten short kernels and the gaps between them are a fifth of its time.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+#ifdef B2D_AB_NOPDL
+  pdl = false;      // A/B timing build
+#endif
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk TMA helpers (sm_90+/sm_100a PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {

@@ -176,6 +176,8 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
                    float4* __restrict__ kept_boxes_all) {
   extern __shared__ __align__(16) unsigned char nms_smem_raw[];
   NmsClusterSmem& S = *reinterpret_cast<NmsClusterSmem*>(nms_smem_raw);
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.y;
   const uint32_t cta = cluster_ctarank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -329,13 +331,15 @@ int launch_nms_sorted(int F, int n, const float* boxes, const int32_t* n_valid, 
     cfg.blockDim = dim3(kNmsThreads);
     cfg.dynamicSmemBytes = sizeof(NmsClusterSmem);
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kClusterCtas;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // the kernel waits for its predecessor itself
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     B2D_CUDA(cudaLaunchKernelEx(&cfg, nms_cluster_kernel, reinterpret_cast<const float4*>(boxes), n, n_valid,
                                 float_floor_of(thresh), max_keep, keep, num_keep, static_cast<float4*>(kept_scratch)));
     B2D_LAUNCHED();

@@ -101,6 +101,13 @@ namespace rows {
 #define B2D_WAIT_NS 0
 #endif
 
+#ifdef B2D_AB_COUNT
+__device__ unsigned long long g_ab_count[8];
+#define B2D_COUNT(i, v) do { if (lane == 0) atomicAdd(&g_ab_count[i], (unsigned long long)(v)); } while (0)
+#else
+#define B2D_COUNT(i, v) do { } while (0)
+#endif
+
 constexpr int kWarps = B2D_WARPS;          // 10 consumers + 2 producers (12 measured 1.2 % faster than 10: 35.8 vs 36.3 us/frame)
 constexpr int kThreads = kWarps * 32;
 constexpr int kCh = 32;            // channels per CTA (lanes)
@@ -304,6 +311,8 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
   extern __shared__ int s_buckets[];   // last CTA of the frame: [split * nb] counts, offsets, fill
   __shared__ int s_last;
   constexpr int NT = kP * S;           // taps per axis
+  pdl_trigger();
+  pdl_wait();
   const int nb = nsteps + 1;
   const int nkey = split * nb;
   const int f = blockIdx.y;
@@ -501,8 +510,11 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
 }
 
 // zero rows of padded list entries (seg mode), one block per (entry, frame)
-__global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, float* __restrict__ out, int32_t* __restrict__ ticket) {
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.y, ri = blockIdx.x;
+  if (ri == 0 && threadIdx.x == 0) ticket[f] = 0;       // (instead of a memset node, which would break the launch chain)
   if (ri < L.seg_count[f]) return;
   const int e = f * L.seg_stride + ri;
   const int r = L.ids ? L.ids[e] : e;
@@ -576,6 +588,9 @@ __device__ __forceinline__ void tile_release(int* locks, int t, int lane) {
 }
 
 __device__ __forceinline__ float lds_at(uint32_t addr) {
+#ifdef B2D_AB_NOTAPS
+  return __uint_as_float(addr);       // A/B timing build: no tap loads
+#endif
   float v;
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));   // not volatile: taps of an item may reorder
   return v;
@@ -714,6 +729,9 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
   float4 e0 = slot[kRowVec0], e1 = slot[kRowVec0 + (RV == 2 ? 1 : 0)];
 #pragma unroll 1
   for (int i = 0; i < nrows; ++i) {
+#ifdef B2D_AB_NOROWS
+    break;                            // A/B timing build: no row loop
+#endif
     const float4 f0 = e0, f1 = e1;
     const uint32_t rv = row_off(f0);
     const uint32_t ro = rv & ((1u << kRowBlkShift) - 1u);
@@ -742,6 +760,7 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
       } else {
         t = tile_try_acquire(locks, npool, warp, lane);
       }
+      B2D_COUNT(t >= 0 ? 0 : 1, 1);
       if (t >= 0) {
         float* tile = pool + (size_t)t * kTileWords;
 #pragma unroll
@@ -750,13 +769,17 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
           for (int pw = 0; pw < kP; ++pw) tile[lane * (kP * kP) + p * kP + pw] = B2D_ACC(p, pw);   // 49 words per lane: odd pitch
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
         __syncwarp();
+#ifndef B2D_AB_NOGLOBAL
         if (lane == 0) bulk_s2g(o, smem_u32(tile), (uint32_t)kTileWords * 4u);
+#endif
         held = t;
         return;
       }
     }
   }
   // results: stage one bin-row [32 ch][7] at a time so that global stores run along (c, pw)
+  B2D_COUNT(2, 1);
+  B2D_COUNT(3, nph);
 #pragma unroll
   for (int p = 0; p < NPH; ++p) {
     if (p >= nph) break;
@@ -766,7 +789,11 @@ __device__ __forceinline__ void run_item(Landed&& wait_row, const float4* __rest
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kP; ++j)
+#ifdef B2D_AB_NOGLOBAL
+      if (omask & (1u << j)) asm volatile("" ::"f"(stage[lane + 32 * j]));     // A/B timing build: everything but the global stores
+#else
       if (omask & (1u << j)) o[p * kP + ooff[j]] = stage[lane + 32 * j];
+#endif
   }
   __syncwarp();
 #undef B2D_ACC
@@ -840,6 +867,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
       ring[(size_t)rc * pitch + x] = 0.0f;
     }
   }
+  pdl_wait();        // (few-frame calls chain their launches: the prologue above overlaps the prep kernel)
   __syncthreads();
 
   if (FILL && warp >= kConsumers) {
@@ -903,6 +931,9 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   if (p2) asm volatile("st.shared.f32 [%0+256], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 2]) : "memory");               \
   if (p3) asm volatile("st.shared.f32 [%0+384], %1;" ::"r"(DJ), "f"(v[(J) * 4 + 3]) : "memory");
       for (int bi = 0; bi < nbat; ++bi) {
+#ifdef B2D_AB_NOREPACK
+        break;                          // A/B timing build: TMA + barrier protocol only
+#endif
         const int c8 = (bi / ncg) * 8, cg = (bi - (bi / ncg) * ncg) * 4;
         const bool p0 = cg + 0 < nchunk - 1 || (cg + 0 == nchunk - 1 && tail_ok);
         const bool p1 = cg + 1 < nchunk - 1 || (cg + 1 == nchunk - 1 && tail_ok);
@@ -1186,6 +1217,17 @@ static bool make_tmap(CUtensorMap* map, const float* feat, int F, int C, int H, 
 
 }  // namespace rows
 
+#ifdef B2D_AB_COUNT
+extern "C" void b2d_ab_counters(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, rows::g_ab_count, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(rows::g_ab_count, z, sizeof(z));
+  }
+}
+#endif
+
 size_t rows_workspace_bytes(int F, int /*H*/, int per_frame) { return rows::carve(nullptr, F, per_frame).bytes; }
 
 // Returns B2D_ERR_UNSUPPORTED when this path does not apply (caller falls back).
@@ -1204,15 +1246,19 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   ws.scale = scale;
   ws.aligned = aligned;
   const int items_cap = per_frame * kP;
-  B2D_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(int32_t) * (size_t)F, st));
-  if (L.seg_count) {
-    dim3 zg(L.seg_stride, F);
-    zero_pad_kernel<<<zg, 256, 0, st>>>(L, C * PH * PW, out);
-    B2D_LAUNCHED();
-  }
   const int groups = ceil_div(C, kCh) * F;
   int split = 1;
   while (split < kMaxSplit && groups * split < 2 * kNumSMs) split *= 2;
+  // few frames per call: the launches are chained programmatically (every kernel waits for its predecessor on the
+  // device), which hides the launch gaps - a fifth of a one-frame call
+  const bool pdl = split > 1;
+  if (L.seg_count) {
+    dim3 zg(L.seg_stride, F);
+    B2D_CUDA(launch_pdl(zero_pad_kernel, zg, dim3(256), 0, st, pdl, L, C * PH * PW, out, ws.ticket));
+    B2D_LAUNCHED();
+  } else {
+    B2D_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(int32_t) * (size_t)F, st));
+  }
   dim3 grid(ceil_div(C, kCh), F, split);
   const int nb = p.nsteps + 1;
   // split > 1 (few frames): each of the `split` CTAs of a (frame, channel group) streams only its band of rows
@@ -1221,12 +1267,14 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   KArgs a{feat, L, C, H, W, p.lane_stride, p.row_words, stage_width(W), p.St, p.nblk, p.nbk, items_cap, band_rows, halo, p.npool, ws, out};
 #define B2D_ROWS(SS, FF)                                                                                          \
   do {                                                                                                            \
-    prep_kernel<SS><<<dim3(ceil_div(per_frame, kPrepWarps), F), kPrepThreads,                                        \
-                      sizeof(int) * (3 * split * nb + (items_cap <= kPrepKeyCache ? items_cap : 0)), st>>>( \
-        L, H, W, scale, aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, per_frame, split, band_rows, ws); \
+    B2D_CUDA(launch_pdl(prep_kernel<SS>, dim3(ceil_div(per_frame, kPrepWarps), F), dim3(kPrepThreads),             \
+                        sizeof(int) * (3 * split * nb + (items_cap <= kPrepKeyCache ? items_cap : 0)), st, pdl, L, H, W, scale, \
+                        aligned, p.Rr, p.St, p.span_max, p.span_whole, p.nsteps, p.row_words * 4, per_frame, split,   \
+                        band_rows, ws));                                                                          \
     B2D_LAUNCHED();                                                                                               \
     B2D_CUDA(cudaFuncSetAttribute(fwd_kernel<SS, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
-    fwd_kernel<SS, FF><<<grid, kThreads, p.smem, st>>>(a, tmap, feat, ws.records, L.rois, out);                    \
+    B2D_CUDA(launch_pdl(fwd_kernel<SS, FF>, grid, dim3(kThreads), p.smem, st, pdl, a, tmap, feat,                  \
+                        (const float4*)ws.records, L.rois, out));                                                 \
     B2D_LAUNCHED();                                                                                               \
   } while (0)
 #define B2D_ROWS_S(FF)           \

@@ -40,4 +40,12 @@ for _ in range(iters):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts.sort()
-print(f"{wl}{' TRAIN' if train else ''}: one frame per call: median {ts[len(ts) // 2]:.4f} ms, min {ts[0]:.4f} ms")
+# the same calls back to back (what bench.py's latency_ms_f1 reports: the GPU never waits for the host)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    one()
+e1.record()
+torch.cuda.synchronize()
+print(f"{wl}{' TRAIN' if train else ''}: one frame per call: synchronised median {ts[len(ts) // 2]:.4f} ms, min {ts[0]:.4f} ms; "
+      f"back to back {e0.elapsed_time(e1) / iters:.4f} ms")
