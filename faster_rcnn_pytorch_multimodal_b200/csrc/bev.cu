@@ -91,6 +91,7 @@ __device__ __forceinline__ int voxel_key(const float* __restrict__ p, const Grid
 }
 
 __global__ void __launch_bounds__(256) key_kernel(int n, const float* __restrict__ pts, Grid g, Ws w) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k = voxel_key(pts + (size_t)i * g.n_feat, g);
@@ -101,6 +102,8 @@ __global__ void __launch_bounds__(256) key_kernel(int n, const float* __restrict
 // warp-aggregated: one atomic per warp on each of the two cursors (100 k voxels on two addresses
 // serialise otherwise: 79 us -> a few us)
 __global__ void __launch_bounds__(256) alloc_kernel(int n, Ws w) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool owner = i < n && w.slot[i] == 0;
@@ -127,6 +130,8 @@ __global__ void __launch_bounds__(256) alloc_kernel(int n, Ws w) {
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(int n, Ws w) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k = w.key[i];
@@ -134,6 +139,8 @@ __global__ void __launch_bounds__(256) fill_kernel(int n, Ws w) {
 }
 
 __global__ void __launch_bounds__(256) first_kernel(Ws w) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const int nvox = w.counters[1];
@@ -154,6 +161,8 @@ __global__ void __launch_bounds__(256) first_kernel(Ws w) {
 // before word wd, so the rank of the voxel that starts at point i is rank[i >> 5] + popc(bits below i).
 // One CTA: a few thousand words.
 __global__ void __launch_bounds__(1024) scan_kernel(int n, Ws w) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int warp_sum[32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nwords = (n + 31) / 32;
@@ -186,6 +195,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(int n, Ws w) {
 
 __global__ void __launch_bounds__(256) voxel_kernel(int n_points, const float* __restrict__ pts, Grid g, Ws w,
                                                      float* __restrict__ out, int32_t* __restrict__ num_voxels_out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const int nvox = w.counters[1];
@@ -247,6 +258,8 @@ __global__ void __launch_bounds__(256) voxel_kernel(int n_points, const float* _
 }
 
 __global__ void __launch_bounds__(256) meta_kernel(Grid g, Ws w, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int nvox = w.counters[1];
   const int C = g.nz + g.n_meta;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
@@ -294,20 +307,22 @@ extern "C" int b2d_bev_rasterize(int num_points, int num_feat, const float* poin
   const bev::Grid g{x_lo, x_hi, y_lo, y_hi, z_lo, z_hi, voxel_len, voxel_height, nx, ny, nz,
                     max_pts_per_voxel, max_voxels, num_meta, elongation, num_feat};
   const int blocks = ceil_div(num_points, 256);
-  bev::key_kernel<<<blocks, 256, 0, st>>>(num_points, points, g, w);
+  // seven short kernels, chained by programmatic dependent launches (each waits for its predecessor on the device:
+  // the launch gaps were a sixth of the call)
+  bev::key_kernel<<<blocks, 256, 0, st>>>(num_points, points, g, w);          // (ordered after the memsets above)
   B2D_LAUNCHED();
-  bev::alloc_kernel<<<blocks, 256, 0, st>>>(num_points, w);
+  B2D_CUDA(launch_pdl(bev::alloc_kernel, dim3(blocks), dim3(256), 0, st, true, num_points, w));
   B2D_LAUNCHED();
-  bev::fill_kernel<<<blocks, 256, 0, st>>>(num_points, w);
+  B2D_CUDA(launch_pdl(bev::fill_kernel, dim3(blocks), dim3(256), 0, st, true, num_points, w));
   B2D_LAUNCHED();
   const int wgrid = min(ceil_div(num_points, 8), 8 * kNumSMs);
-  bev::first_kernel<<<wgrid, 256, 0, st>>>(w);
+  B2D_CUDA(launch_pdl(bev::first_kernel, dim3(wgrid), dim3(256), 0, st, true, w));
   B2D_LAUNCHED();
-  bev::scan_kernel<<<1, 1024, 0, st>>>(num_points, w);
+  B2D_CUDA(launch_pdl(bev::scan_kernel, dim3(1), dim3(1024), 0, st, true, num_points, w));
   B2D_LAUNCHED();
-  bev::voxel_kernel<<<wgrid, 256, 0, st>>>(num_points, points, g, w, bev_map, num_voxels);
+  B2D_CUDA(launch_pdl(bev::voxel_kernel, dim3(wgrid), dim3(256), 0, st, true, num_points, points, g, w, bev_map, num_voxels));
   B2D_LAUNCHED();
-  bev::meta_kernel<<<min(blocks, 4 * kNumSMs), 256, 0, st>>>(g, w, bev_map);
+  B2D_CUDA(launch_pdl(bev::meta_kernel, dim3(min(blocks, 4 * kNumSMs)), dim3(256), 0, st, true, g, w, bev_map));
   B2D_LAUNCHED();
   return B2D_OK;
 }
