@@ -510,9 +510,12 @@ prep_kernel(RoiList L, int H, int W, float scale, int aligned, int Rr, int St, i
 }
 
 // zero rows of padded list entries (seg mode), one block per (entry, frame)
-__global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, float* __restrict__ out, int32_t* __restrict__ ticket) {
-  pdl_trigger();
-  pdl_wait();
+__global__ void __launch_bounds__(256) zero_pad_kernel(RoiList L, int per_roi, float* __restrict__ out, int32_t* __restrict__ ticket,
+                                                       int pdl) {
+  if (pdl) {       // (one CTA per list entry, nearly all of which leave at once: with many frames the wait is not free)
+    pdl_trigger();
+    pdl_wait();
+  }
   const int f = blockIdx.y, ri = blockIdx.x;
   if (ri == 0 && threadIdx.x == 0) ticket[f] = 0;       // (instead of a memset node, which would break the launch chain)
   if (ri < L.seg_count[f]) return;
@@ -1254,7 +1257,7 @@ int roi_align_forward_rows(int F, int C, int H, int W, const float* feat, const 
   const bool pdl = split > 1;
   if (L.seg_count) {
     dim3 zg(L.seg_stride, F);
-    B2D_CUDA(launch_pdl(zero_pad_kernel, zg, dim3(256), 0, st, pdl, L, C * PH * PW, out, ws.ticket));
+    B2D_CUDA(launch_pdl(zero_pad_kernel, zg, dim3(256), 0, st, pdl, L, C * PH * PW, out, ws.ticket, pdl ? 1 : 0));
     B2D_LAUNCHED();
   } else {
     B2D_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(int32_t) * (size_t)F, st));

@@ -70,7 +70,7 @@ def main():
             step_total += mean
     for k in summ:
         summ[k]["share_of_step"] = round(summ[k]["mean_us"] / step_total, 4)
-    json.dump({"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 "
+    json.dump({"command": "ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'b2d|rows::' -c 600 python bench.py --steps 2 "
                           "--warmup 3 --no-cpu-baseline --no-gpu-baseline",
                "note": "cold-cache, serialised per-launch times; launches whose grid spans all %d frames of a step are the "
                        "timed path, the others belong to the e2e host-buffer leg, the F = 1 latency leg and the parity gate" % F,
@@ -83,12 +83,13 @@ def main():
         if not os.path.exists(path):
             continue
         Lf = launches(path)
-        # the last iteration: from the last score_hist launch on
-        idx = max(i for i, l in enumerate(Lf) if "score_hist" in l[0])
+        # the last iteration: from the last select launch on (the first kernel of a call)
+        first = lambda l: "select_fused" in l[0] or "score_hist" in l[0]
+        idx = max(i for i, l in enumerate(Lf) if first(l))
         it = Lf[idx:]
         # RoIAlign launches of that iteration follow in the list only if the script ends with them: take one full cycle
         names = [short(l[0]) for l in Lf]
-        cyc_start = max(i for i in range(idx) if "score_hist" in Lf[i][0]) if any("score_hist" in l[0] for l in Lf[:idx]) else idx
+        cyc_start = max(i for i in range(idx) if first(Lf[i])) if any(first(l) for l in Lf[:idx]) else idx
         cyc = Lf[cyc_start:idx]
         f1[tag] = {"kernels": [{"kernel": short(n), "grid": g, "block": b, "us": round(us, 2)} for n, g, b, us in cyc],
                    "sum_us": round(sum(us for *_, us in cyc), 1)}
