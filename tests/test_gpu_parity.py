@@ -342,6 +342,50 @@ def test_proposal_batched_matches_single_frame():
         assert (rois[f, :n, 0] == f).all() and (rois[f, n:] == 0).all()
 
 
+def test_proposal_many_frame_path_matches_few_frame_path():
+    """More than 8 frames per call take the histogram / threshold / compact / in-CTA sort / single-CTA NMS kernels, up to 8 the
+    fused cooperative select, run sort + binary-search ranking and the cluster NMS: two implementations, one result."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    Hf, Wf, A, F = 40, 60, 25, 11
+    prob, deltas = synth_rpn(21, Hf, Wf, A, F=F)
+    prob[3] = (prob[3] * 8).round() / 8                    # one frame with thousands of ties at the cut
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0]).to(dev())
+    info = torch.tensor([[0, 960, 0, 640, 0, 0, 1.0]]).repeat(F, 1).to(dev())
+    for pre, post in ((6000, 300), (12000, 2000)):
+        rois, sc, _, aidx, num = ops.proposal_batched(prob.to(dev()), deltas.to(dev()), info, anchors, None, A, pre, post,
+                                                      0.7, batch_index_stride=1, want_anchor_index=True)
+        for f0 in range(0, F, 4):
+            f1 = min(F, f0 + 4)
+            r1, s1, _, a1, n1 = ops.proposal_batched(prob[f0:f1].to(dev()), deltas[f0:f1].to(dev()), info[f0:f1], anchors, None,
+                                                     A, pre, post, 0.7, batch_index_stride=1, want_anchor_index=True)
+            assert torch.equal(num[f0:f1], n1)
+            assert torch.equal(rois[f0:f1, :, 1:], r1[:, :, 1:]) and torch.equal(sc[f0:f1], s1)
+            assert torch.equal(aidx[f0:f1], a1)
+
+
+def test_nms_single_cta_and_cluster_kernels_agree():
+    """The same clustered boxes through the single-CTA kernel (more than 8 frames) and the cluster kernel (one frame at a time),
+    with and without a post-NMS cap that falls inside a tile."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    F, n = 10, 3000
+    ctr = torch.rand(F, 40, 2, generator=g) * 800
+    pick = torch.randint(0, 40, (F, n), generator=g)
+    c = torch.gather(ctr, 1, pick[..., None].expand(F, n, 2)) + torch.randn(F, n, 2, generator=g) * 12
+    wh = 40 + torch.rand(F, n, 2, generator=g) * 60
+    boxes = torch.cat([c - wh / 2, c + wh / 2], dim=2).to(dev())
+    for cap in (-1, 37, 300):
+        keep, num = ops.nms_sorted(boxes, 0.7, max_keep=cap)
+        for f in range(F):
+            k1, n1 = ops.nms_sorted(boxes[f:f + 1], 0.7, max_keep=cap)
+            assert int(num[f]) == int(n1[0])
+            assert torch.equal(keep[f, :int(num[f])], k1[0, :int(n1[0])])
+        want = O.nms(boxes[0].cpu(), torch.arange(n, 0, -1).float(), 0.7)
+        if cap > 0:
+            want = want[:cap]
+        assert torch.equal(keep[0, :int(num[0])].cpu().long(), want)
+
+
 def test_proposal_top_layer_golden(golden):
     from faster_rcnn_pytorch_multimodal_b200.layer_utils.proposal_top_layer import proposal_top_layer
     from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
