@@ -110,7 +110,10 @@ __device__ unsigned long long g_ab_count[8];
 
 constexpr int kWarps = B2D_WARPS;          // 10 consumers + 2 producers (12 measured 1.2 % faster than 10: 35.8 vs 36.3 us/frame)
 constexpr int kThreads = kWarps * 32;
-constexpr int kCh = 32;            // channels per CTA (lanes)
+#ifndef B2D_AB_CH
+#define B2D_AB_CH 32
+#endif
+constexpr int kCh = B2D_AB_CH;     // channels per CTA (lanes); the A/B value 16 only makes sense in the skeleton builds (fill cost of half-size rows)
 constexpr int kP = 7;              // PH = PW = 7
 constexpr int kRecVec = 32;        // float4 per item record
 constexpr int kRecBytes = kRecVec * 16;
@@ -128,7 +131,7 @@ constexpr int kPoolRingRows = 12;
 // per consumer warp: its record slot (512 B), overlaid by its bin-row output tile [32 ch][7] (896 B) - the record is
 // dead once the row loop of an item has finished
 constexpr int kWarpAreaBytes = kCh * kP * 4 > kRecBytes ? kCh * kP * 4 : kRecBytes;
-constexpr int kTileWords = kCh * kP * kP;
+constexpr int kTileWords = (kCh * kP * kP + 31) / 32 * 32;      // (1568 for 32 channels; rounded so that what follows stays 128-byte aligned)
 constexpr int kStages = B2D_STAGES;         // staging rows of the TMA fill
 constexpr int kProducers = 2;               // producer warps of the TMA fill (each repacks 32 / kProducers channels)
 
@@ -174,6 +177,7 @@ static Plan make_plan(int H, int W, bool allow_tma) {
   const size_t fixed = fixed_for(p.npool);
   if (fixed + 6 * row_bytes > budget) { p.ok = false; return p; }
   int Rr = (int)((budget - fixed) / row_bytes);
+  while (Rr > 6 && ((size_t)Rr * row_bytes) % 128 != 0) --Rr;      // what follows the ring stays 128-byte aligned (a no-op for 32 channels)
   if (Rr >= H) {
     p.Rr = H; p.St = H; p.nblk = 1; p.nbk = 1; p.span_max = H; p.nsteps = 1;
   } else {
