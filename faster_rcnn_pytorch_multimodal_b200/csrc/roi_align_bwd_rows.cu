@@ -30,7 +30,8 @@ constexpr int kMaxWarps = 16;
 #ifndef B2D_BWD_TILE
 #define B2D_BWD_TILE 4
 #endif
-constexpr int kTile = B2D_BWD_TILE;                  // RoI tiles per batch (two batches in flight)
+constexpr int kTile = B2D_BWD_TILE;                  // (smem sizing: 2 * kTile slots)
+constexpr int kSlots = 2 * kTile;                    // RoI slices in flight (ring of single-RoI slots)
 constexpr int kTileWords = kCh * kP * kP; // 1568 floats = 6272 bytes
 
 struct Plan {
@@ -45,12 +46,12 @@ static Plan make_plan(int H, int W) {
   const size_t row_bytes = (size_t)kCh * p.pitch * 4;
   const size_t tiles = (size_t)2 * kTile * (kTileWords * 4 + kTabVec * 16);
   int band = (int)((227 * 1024 - 4096 - tiles) / row_bytes);
-  if (band > kMaxWarps) band = kMaxWarps;
+  if (band > kMaxWarps - 1) band = kMaxWarps - 1;
   if (band > H) band = H;
   if (band < 2) { p.ok = false; return p; }
   p.nbands = ceil_div(H, band);
   p.band = ceil_div(H, p.nbands);          // balance the bands
-  p.warps = p.band;                        // one warp per row
+  p.warps = p.band + 1;                    // one warp per row + the warp that feeds the slice ring
   p.smem = (size_t)p.band * row_bytes + tiles + 128;
   p.ok = true;
   return p;
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, int pitch, int band, int accumulate,
            int use_tma, const float4* __restrict__ tab, float* __restrict__ grad_feat) {
   extern __shared__ __align__(16) float acc[];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_full[kSlots];    // slice + table of the slot have landed (TMA bytes)
+  __shared__ __align__(8) uint64_t s_empty[kSlots];   // every row warp is done with the slot
   __shared__ int s_list[kMaxWarps * 32];   // list entries of the current chunk that touch the band, in index order
   __shared__ int s_warp_cnt[kMaxWarps];
   const int f = blockIdx.z;
@@ -106,18 +108,20 @@ bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, i
   const int rows = min(band, H - y0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarp = blockDim.x >> 5;
+  const int nrow_warps = nwarp - 1;                     // warps 0 .. nrow_warps-1 own a row, the last warp feeds the ring
   const int nch = min(kCh, C - c0);
   const bool ch_ok = lane < nch;
   constexpr int bins = kP * kP;
   const int row_words = kCh * pitch;
   for (int i = tid; i < rows * row_words; i += blockDim.x) acc[i] = 0.0f;
-  float* tiles = acc + (size_t)band * row_words;       // [2][kTile][32 ch][49] grad_out slices ...
-  float4* tabs = reinterpret_cast<float4*>(tiles + (size_t)2 * kTile * kTileWords);   // ... and [2][kTile][29] RoI tables
+  float* tiles = acc + (size_t)band * row_words;       // [kSlots][32 ch][49] grad_out slices ...
+  float4* tabs = reinterpret_cast<float4*>(tiles + (size_t)kSlots * kTileWords);   // ... and [kSlots][29] RoI tables
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], nrow_warps);
+    }
   }
-  int phase0 = 0, phase1 = 0;
 
   int first = 0, n_ent = L.n;
   if (L.seg_count) {
@@ -126,8 +130,14 @@ bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, i
   }
   const int my_row = y0 + warp;                         // the row this warp owns (may be >= H: idle)
   const bool row_ok = warp < rows;
-  float* my_acc = acc + (size_t)warp * row_words + (size_t)lane * pitch;
+  float* my_acc = acc + (size_t)min(warp, band - 1) * row_words + (size_t)lane * pitch;
   const uint32_t my_acc_s = smem_u32(my_acc);
+  // Slices travel through a ring of kSlots single-RoI slots handed over with mbarriers only: the feeding warp refills a
+  // slot as soon as every row warp has left it, and a row warp that a RoI does not touch moves straight on to the next
+  // one.  (Batches of four RoIs between CTA-wide barriers left the warps waiting for the busiest row of each batch:
+  // 2.7 of 8.3 stall cycles per issued instruction.)  `g` counts the RoIs of all chunks: slot = g % kSlots,
+  // use = g / kSlots gives the barrier parities on both sides.
+  int g = 0;
 
   for (int base = 0; base < n_ent; base += (int)blockDim.x) {
     // ---- ordered list of the entries of this chunk (one per thread) that touch the band
@@ -154,32 +164,27 @@ bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, i
     if (t) s_list[before + __popc(bal & ((1u << lane) - 1u))] = first + i;
     __syncthreads();
     const int n_list = total;
-    // ---- batches of kTile RoIs: grad_out slices by bulk TMA (two batches in flight), then every warp
-    // walks the batch in list order and accumulates into its own row
-    const int n_batch = (n_list + kTile - 1) / kTile;
-    auto issue = [&](int b) {            // one thread: slices + tables of batch b -> stage b & 1
-      const int l0 = b * kTile, l1 = min(n_list, l0 + kTile);
-      uint64_t* bar = &s_bar[b & 1];
-      mbar_expect_tx(bar, (uint32_t)(l1 - l0) * (uint32_t)((use_tma ? kTileWords * 4 : 0) + kTabVec * 16));
-      for (int li = l0; li < l1; ++li) {
-        const int e = s_list[li];
-        const int r = L.ids ? L.ids[e] : e;
-        const int slot = (b & 1) * kTile + (li - l0);
-        if (use_tma)
-          bulk_g2s(tiles + (size_t)slot * kTileWords, grad_out + ((size_t)r * C + c0) * bins, (uint32_t)(kTileWords * 4), bar);
-        bulk_g2s(tabs + (size_t)slot * kTabVec, tab + (size_t)e * kTabVec, (uint32_t)(kTabVec * 16), bar);
+    if (warp == nrow_warps) {
+      // ---- feeder: one bulk TMA per slice (+ its table), as far ahead as the ring allows
+      if (lane == 0) {
+        for (int li = 0; li < n_list; ++li) {
+          const int gi = g + li, slot = gi % kSlots, use = gi / kSlots;
+          mbar_wait(&s_empty[slot], (uint32_t)((use & 1) ^ 1));      // (a fresh barrier passes the first round)
+          const int e = s_list[li];
+          const int r = L.ids ? L.ids[e] : e;
+          uint64_t* bar = &s_full[slot];
+          mbar_expect_tx(bar, (uint32_t)((use_tma ? kTileWords * 4 : 0) + kTabVec * 16));
+          if (use_tma)
+            bulk_g2s(tiles + (size_t)slot * kTileWords, grad_out + ((size_t)r * C + c0) * bins, (uint32_t)(kTileWords * 4), bar);
+          bulk_g2s(tabs + (size_t)slot * kTabVec, tab + (size_t)e * kTabVec, (uint32_t)(kTabVec * 16), bar);
+        }
       }
-    };
-    if (tid == 0) {
-      if (n_batch > 0) issue(0);
-      if (n_batch > 1) issue(1);
-    }
-    for (int b = 0; b < n_batch; ++b) {
-      mbar_wait(&s_bar[b & 1], (uint32_t)((((b & 1) ? phase1 : phase0) + (b >> 1)) & 1));
-      if (row_ok) {
-        const int l1 = min(n_list, (b + 1) * kTile);
-        for (int li = b * kTile; li < l1; ++li) {
-          const int slot = (b & 1) * kTile + (li - b * kTile);
+    } else {
+      // ---- row warps: walk the list in order, each accumulating into its own row
+      for (int li = 0; li < n_list; ++li) {
+        const int gi = g + li, slot = gi % kSlots, use = gi / kSlots;
+        mbar_wait(&s_full[slot], (uint32_t)(use & 1));
+        if (row_ok) {
           const float4* t = tabs + (size_t)slot * kTabVec;
           // lane k tests sample row k of this RoI against my row
           float wy = 0.0f;
@@ -189,46 +194,46 @@ bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, i
             if (__float_as_int(yr.y) == my_row && __float_as_int(yr.y) != __float_as_int(yr.x)) wy += yr.w;
           }
           unsigned hits = __ballot_sync(0xffffffffu, wy != 0.0f);
-          if (!hits) continue;
-          // samples that land on my row -> T[pw]
-          float T[kP];
+          if (hits) {
+            // samples that land on my row -> T[pw]
+            float T[kP];
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) T[pw] = 0.0f;
-          const float* gt = tiles + (size_t)slot * kTileWords + lane * bins;
-          const int e = s_list[li];
-          const int r = L.ids ? L.ids[e] : e;
-          const float* go = grad_out + ((size_t)r * C + c0 + (ch_ok ? lane : 0)) * bins;
-          while (hits) {
-            const int k = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const float w = __shfl_sync(0xffffffffu, wy, k);
-            const int ph = S == 2 ? k >> 1 : k;
+            for (int pw = 0; pw < kP; ++pw) T[pw] = 0.0f;
+            const float* gt = tiles + (size_t)slot * kTileWords + lane * bins;
+            const int e = s_list[li];
+            const int r = L.ids ? L.ids[e] : e;
+            const float* go = grad_out + ((size_t)r * C + c0 + (ch_ok ? lane : 0)) * bins;
+            while (hits) {
+              const int k = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const float w = __shfl_sync(0xffffffffu, wy, k);
+              const int ph = S == 2 ? k >> 1 : k;
 #pragma unroll
-            for (int pw = 0; pw < kP; ++pw) {
-              const float g = use_tma ? gt[ph * kP + pw] : (ch_ok ? __ldg(go + ph * kP + pw) : 0.0f);
-              T[pw] = fmaf(g, w, T[pw]);
+              for (int pw = 0; pw < kP; ++pw) {
+                const float gv = use_tma ? gt[ph * kP + pw] : (ch_ok ? __ldg(go + ph * kP + pw) : 0.0f);
+                T[pw] = fmaf(gv, w, T[pw]);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kP * S; ++k) {
+              const float4 x4 = t[1 + 2 * kP + k];
+              const float gv = T[S == 2 ? k >> 1 : k];
+              const uint32_t a = my_acc_s + (uint32_t)__float_as_int(x4.x);
+              float v0, v1;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
+              asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v1) : "r"(a));
+              v0 = fmaf(gv, x4.y, v0);
+              v1 = fmaf(gv, x4.z, v1);
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v0) : "memory");
+              asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(a), "f"(v1) : "memory");
             }
           }
-#pragma unroll
-          for (int k = 0; k < kP * S; ++k) {
-            const float4 x4 = t[1 + 2 * kP + k];
-            const float g = T[S == 2 ? k >> 1 : k];
-            const uint32_t a = my_acc_s + (uint32_t)__float_as_int(x4.x);
-            float v0, v1;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
-            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v1) : "r"(a));
-            v0 = fmaf(g, x4.y, v0);
-            v1 = fmaf(g, x4.z, v1);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v0) : "memory");
-            asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(a), "f"(v1) : "memory");
-          }
         }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[slot])) : "memory");
       }
-      __syncthreads();                                     // everyone is done with stage b & 1
-      if (tid == 0 && b + 2 < n_batch) issue(b + 2);
     }
-    phase0 += (n_batch + 1) >> 1;                          // completed phases of s_bar[0] ...
-    phase1 += n_batch >> 1;                                // ... and of s_bar[1]
+    g += n_list;
   }
   __syncthreads();
   // ---- write-out: lanes sweep x, (channel, row) pairs over the warps
