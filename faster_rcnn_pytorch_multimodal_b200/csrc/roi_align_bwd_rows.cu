@@ -219,6 +219,8 @@ bwd_kernel(const float* __restrict__ grad_out, RoiList L, int C, int H, int W, i
               const float4 x4 = t[1 + 2 * kP + k];
               const float gv = T[S == 2 ? k >> 1 : k];
               const uint32_t a = my_acc_s + (uint32_t)__float_as_int(x4.x);
+              // (shared-memory reductions instead of this read-modify-write - red.shared.add.f32, no load -> FMA -> store
+              // chain - measured 1.71 ms against 1.07 for 8 x 256 RoIs: rejected)
               float v0, v1;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
               asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v1) : "r"(a));
