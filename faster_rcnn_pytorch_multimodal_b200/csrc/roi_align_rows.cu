@@ -94,12 +94,7 @@ namespace rows {
 #ifndef B2D_L2_AHEAD
 #define B2D_L2_AHEAD 2
 #endif
-#ifndef B2D_POLL_NS
-#define B2D_POLL_NS 64
-#endif
-#ifndef B2D_WAIT_NS
-#define B2D_WAIT_NS 0
-#endif
+#define B2D_POLL_NS 64       // producers' back-off between two looks at the consumers' progress (256 / 1024 ns measured +0.4 % / +2.3 %)
 
 #ifdef B2D_AB_COUNT
 __device__ unsigned long long g_ab_count[8];
@@ -1028,11 +1023,7 @@ fwd_kernel(const __grid_constant__ KArgs a, const __grid_constant__ CUtensorMap 
   };
   auto wait_on = [&](uint64_t* bar, uint32_t parity) {
     if (FILL) {
-      if (B2D_WAIT_NS > 0) {
-        while (!mbar_test(bar, parity)) __nanosleep(B2D_WAIT_NS);
-      } else {
-        mbar_wait(bar, parity);
-      }
+      mbar_wait(bar, parity);       // (a nanosleep back-off here measured +0.3 %)
     } else {
       while (!mbar_test(bar, parity)) pump();
     }
