@@ -563,6 +563,38 @@ def test_roi_align_multi_frame_and_padded_segments():
     close(got.view(F, M, C, 7, 7), want, atol=1e-5)
 
 
+def test_roi_align_backward_long_lists_over_frames():
+    """Backward with more list entries than one CTA scans at a time (several chunks feed the slice ring back to back) on an
+    unsegmented three-frame list, and the same RoIs in the padded per-frame layout."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    F, C, H, W, R = 3, 40, 24, 78, 1500
+    g = torch.Generator().manual_seed(12)
+    feat = torch.randn(F, C, H, W, generator=g)
+    rois = _random_rois(31, R, W * 16, H * 16, F=F)
+    f_ref = feat.clone().requires_grad_(True)
+    want = O.roi_align(f_ref, rois, (7, 7), 1.0 / 16, 2, False)
+    gout = torch.randn(want.shape, generator=g)
+    want.backward(gout)
+    tol = 1e-5 * float(f_ref.grad.abs().max())
+    got = ops._roi_align_backward(gout.to(dev()), rois.to(dev()), (F, C, H, W), (7, 7), 1.0 / 16, 2, False)
+    close(got, f_ref.grad, atol=tol)
+    # padded per-frame layout: the entries sorted by frame, frame f owns rows [f*M, f*M + cnt[f])
+    order = torch.argsort(rois[:, 0], stable=True)
+    cnt = torch.bincount(rois[:, 0].long(), minlength=F).to(torch.int32)
+    M = int(cnt.max())
+    seg = torch.zeros(F, M, 5)
+    gseg = torch.zeros(F, M, C, 7, 7)
+    o = 0
+    for f in range(F):
+        n = int(cnt[f])
+        seg[f, :n] = rois[order[o:o + n]]
+        gseg[f, :n] = gout[order[o:o + n]]
+        o += n
+    got = ops._roi_align_backward(gseg.view(-1, C, 7, 7).to(dev()), seg.view(-1, 5).to(dev()), (F, C, H, W), (7, 7), 1.0 / 16, 2,
+                                  False, seg_count=cnt.to(dev()), seg_stride=M)
+    close(got, f_ref.grad, atol=tol)
+
+
 def test_roi_align_backward_is_deterministic():
     from faster_rcnn_pytorch_multimodal_b200 import ops
     g = torch.Generator().manual_seed(8)
