@@ -427,7 +427,8 @@ def workload_config(cfg, F, parallelism):
 
 
 def add_cpu_baseline(line, args, cfg):
-    if args.no_cpu_baseline:
+    # rank 0 at N = 1 only: under torchrun the other ranks would idle meanwhile and OMP_NUM_THREADS is pinned to 1
+    if args.no_cpu_baseline or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return
     threads = os.cpu_count() or 1
     ref, src = load_reference()
