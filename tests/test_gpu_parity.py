@@ -431,6 +431,28 @@ def test_nms_single_cta_and_cluster_kernels_agree():
         assert torch.equal(keep[0, :int(num[0])].cpu().long(), want)
 
 
+def test_nms_dependency_chains_and_degenerate_tiles():
+    """Worst cases for the fixed-point tile resolve: a chain in which every box suppresses only its successor (the keep set of a
+    tile of 64 needs 32 rounds), identical boxes (one survivor), disjoint boxes (all survive), through both kernels."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    n = 700
+    i = torch.arange(n, dtype=torch.float32)
+    chain = torch.stack((i * 15, torch.zeros(n), i * 15 + 100, torch.full((n,), 50.0)), 1)      # IoU(i, i+1) = 0.74, IoU(i, i+2) = 0.54
+    same = torch.tensor([[10.0, 10.0, 60.0, 80.0]]).repeat(n, 1)
+    apart = torch.stack((i * 200, torch.zeros(n), i * 200 + 100, torch.full((n,), 50.0)), 1)
+    mixed = torch.cat((chain[:300], same[:100], apart[:300]))
+    for boxes in (chain, same, apart, mixed):
+        want = O.nms(boxes, torch.arange(n, 0, -1).float(), 0.7)
+        for F in (1, 9):                                   # cluster kernel / single-CTA kernel
+            b = boxes[None].repeat(F, 1, 1).to(dev())
+            for cap in (-1, 33):
+                keep, num = ops.nms_sorted(b, 0.7, max_keep=cap)
+                w = want if cap < 0 else want[:cap]
+                for f in (0, F - 1):
+                    assert int(num[f]) == w.numel()
+                    assert torch.equal(keep[f, :w.numel()].cpu().long(), w)
+
+
 def test_proposal_top_layer_golden(golden):
     from faster_rcnn_pytorch_multimodal_b200.layer_utils.proposal_top_layer import proposal_top_layer
     from faster_rcnn_pytorch_multimodal_b200.model.config import cfg
