@@ -387,6 +387,34 @@ def test_proposal_few_frame_edge_shapes(Hf, Wf, A, F, pre, post):
         assert (rois[f, :n, 0] == f).all() and (rois[f, n:] == 0).all()
 
 
+@pytest.mark.parametrize("F", [1, 10])
+def test_proposal_selection_with_special_scores(F):
+    """NaN, +-inf, negative and denormal scores: the selection follows torch.sort(descending=True, stable=True) (NaN first), on
+    the few-frame and the many-frame path."""
+    from faster_rcnn_pytorch_multimodal_b200 import ops
+    Hf, Wf, A = 20, 30, 9
+    N = Hf * Wf * A
+    g = torch.Generator().manual_seed(77)
+    prob = torch.randn(F, Hf, Wf, 2 * A, generator=g)
+    flat = prob.view(F, -1)
+    idx = torch.randint(0, flat.shape[1], (F, 400), generator=g)
+    special = torch.tensor([float('nan'), float('inf'), -float('inf'), 0.0, -0.0, 1e-42, -1e-42, 3.0e38])
+    for f in range(F):
+        flat[f, idx[f]] = special[torch.randint(0, special.numel(), (400,), generator=g)]
+    deltas = torch.zeros(F, Hf, Wf, 4 * A)
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, FORK_SCALES, FORK_RATIOS, 1.0)[0])
+    anchors = anchors.view(Hf * Wf, -1, 4)[:, :A].reshape(N, 4).contiguous()
+    info = torch.tensor([[0, Wf * 16.0, 0, Hf * 16.0, 0, 0, 1.0]]).repeat(F, 1)
+    pre = 1500
+    ops.proposal_batched(prob.to(dev()), deltas.to(dev()), info.to(dev()), anchors.to(dev()), None, A, pre, 300, 0.7)
+    sb, ss, si = ops.proposal_sorted_debug(F, Hf * Wf, A, pre, 300, dev())
+    for f in range(F):
+        scores = prob[f, :, :, A:].contiguous().view(-1)
+        o_scores, o_order = scores.sort(descending=True, stable=True)
+        assert torch.equal(si[f].cpu().long(), o_order[:pre])
+        assert torch.equal(ss[f].cpu().view(torch.int32), o_scores[:pre].view(torch.int32))
+
+
 def test_proposal_many_frame_path_matches_few_frame_path():
     """More than 8 frames per call take the histogram / threshold / compact / in-CTA sort / single-CTA NMS kernels, up to 8 the
     fused cooperative select, run sort + binary-search ranking and the cluster NMS: two implementations, one result."""
