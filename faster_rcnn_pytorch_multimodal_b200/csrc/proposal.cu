@@ -409,6 +409,93 @@ __device__ void bitonic_sort_desc(uint64_t* s, int n_pad) {
   }
 }
 
+// The same network for n_pad = 1024 * E keys and 1024 threads, with most of it off shared memory: thread t owns keys
+// [t * E, (t + 1) * E), so the steps with stride j < E are register compare-exchanges, the steps with E <= j < 32 E
+// exchange with a lane of the same warp by shuffle, and only the strides j >= 32 E go through shared memory.  For 8192
+// keys that is 15 shared-memory steps with a CTA barrier instead of 91 (the barrier-per-step form was bound by
+// shared-memory latency: 10 of 17 stall cycles per issued instruction in sort_decode_kernel).
+template <int E>
+__device__ void bitonic_sort_desc_1024(uint64_t* s) {
+  constexpr int n_pad = 1024 * E;
+  const int t = threadIdx.x, lane = t & 31, base = t * E;
+  uint64_t v[E];
+  auto load = [&]() {
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = s[base + e];
+  };
+  auto store = [&]() {
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[base + e] = v[e];
+  };
+  // strides below E: both keys in this thread (J compile-time, k decides the direction of the pair's run)
+  auto local_steps = [&](int k, int jmax) {
+#pragma unroll
+    for (int j = E / 2; j >= 1; j >>= 1) {
+      if (j > jmax) continue;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & j) == 0) {
+          const bool desc = ((base + e) & k) == 0;
+          const uint64_t a = v[e], b = v[e | j];
+          if ((a < b) == desc) {
+            v[e] = b;
+            v[e | j] = a;
+          }
+        }
+      }
+    }
+  };
+  // strides E * m, m < 32: the partner key sits in lane ^ m at the same register index
+  auto shuffle_steps = [&](int k, int mmax) {
+    for (int m = mmax; m >= 1; m >>= 1) {
+      const bool lower = (lane & m) == 0;
+      const bool desc = (base & k) == 0;               // (k >= 2 E here: the whole thread lies in one run)
+      const bool want_max = lower == desc;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, v[e], m);
+        v[e] = want_max ? (o > v[e] ? o : v[e]) : (o < v[e] ? o : v[e]);
+      }
+    }
+  };
+  load();
+  // runs up to 32 E: registers and shuffles only
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+    if (k >= 2 * E) shuffle_steps(k, k / (2 * E));
+    local_steps(k, k / 2);
+  }
+  store();
+  __syncthreads();
+  for (int k = 64 * E; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j >= 32 * E; j >>= 1) {
+      for (int p = t; p < n_pad / 2; p += 1024) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int q = i | j;
+        const uint64_t a = s[i], b = s[q];
+        const bool desc = (i & k) == 0;
+        if ((a < b) == desc) {
+          s[i] = b;
+          s[q] = a;
+        }
+      }
+      __syncthreads();
+    }
+    load();
+    shuffle_steps(k, 16);
+    local_steps(k, E / 2);
+    store();
+    __syncthreads();
+  }
+}
+
+// n_pad keys, 1024 threads: the register / shuffle form when the list fills the CTA, the plain form otherwise
+__device__ __forceinline__ void bitonic_sort_desc_cta(uint64_t* s, int n_pad) {
+  if (blockDim.x == 1024 && n_pad == 16384) bitonic_sort_desc_1024<16>(s);
+  else if (blockDim.x == 1024 && n_pad == 8192) bitonic_sort_desc_1024<8>(s);
+  else if (blockDim.x == 1024 && n_pad == 4096) bitonic_sort_desc_1024<4>(s);
+  else bitonic_sort_desc(s, n_pad);
+}
+
 // Slow path (more than kMaxSortElems candidates, e.g. massive score ties): exact MSB radix
 // select of the k-th largest composite over the global candidate list; returns it.
 __device__ uint64_t radix_select_kth(const uint64_t* __restrict__ cand, int m, int k, uint32_t* hist256,
@@ -510,7 +597,7 @@ __global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a, const u
   while (n_pad < cnt) n_pad <<= 1;
   for (int i = cnt + threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = 0ull;  // below every real key
   __syncthreads();
-  bitonic_sort_desc(keys, n_pad);
+  bitonic_sort_desc_cta(keys, n_pad);
 
   if (threadIdx.x == 0) n_sorted[f] = k;
   float* ob = sorted_boxes + (size_t)f * k_cap * 4;
@@ -680,7 +767,7 @@ __global__ void __launch_bounds__(1024) chunk_sort_kernel(uint64_t* __restrict__
   while (n_pad < cnt) n_pad <<= 1;
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = i < cnt ? g[i] : 0ull;
   __syncthreads();
-  bitonic_sort_desc(keys, n_pad);
+  bitonic_sort_desc_cta(keys, n_pad);
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) g[i] = keys[i];
 }
 
@@ -834,7 +921,7 @@ __global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restr
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
     keys[i] = i < n ? composite_key(score_key(scores[(size_t)f * n + i]), (uint32_t)i) : 0ull;
   __syncthreads();
-  bitonic_sort_desc(keys, n_pad);
+  bitonic_sort_desc_cta(keys, n_pad);
   for (int i = threadIdx.x; i < n; i += blockDim.x) order[(size_t)f * n + i] = (int32_t)composite_index(keys[i]);
 }
 
