@@ -409,14 +409,14 @@ __device__ void bitonic_sort_desc(uint64_t* s, int n_pad) {
   }
 }
 
-// The same network for n_pad = 1024 * E keys and 1024 threads, with most of it off shared memory: thread t owns keys
+// The same network for n_pad = THREADS * E keys, with most of it off shared memory: thread t owns keys
 // [t * E, (t + 1) * E), so the steps with stride j < E are register compare-exchanges, the steps with E <= j < 32 E
 // exchange with a lane of the same warp by shuffle, and only the strides j >= 32 E go through shared memory.  For 8192
 // keys that is 15 shared-memory steps with a CTA barrier instead of 91 (the barrier-per-step form was bound by
 // shared-memory latency: 10 of 17 stall cycles per issued instruction in sort_decode_kernel).
-template <int E>
-__device__ void bitonic_sort_desc_1024(uint64_t* s) {
-  constexpr int n_pad = 1024 * E;
+template <int E, int THREADS>
+__device__ void bitonic_sort_desc_regs(uint64_t* s) {
+  constexpr int n_pad = THREADS * E;
   const int t = threadIdx.x, lane = t & 31, base = t * E;
   uint64_t v[E];
   auto load = [&]() {
@@ -468,7 +468,7 @@ __device__ void bitonic_sort_desc_1024(uint64_t* s) {
   __syncthreads();
   for (int k = 64 * E; k <= n_pad; k <<= 1) {
     for (int j = k >> 1; j >= 32 * E; j >>= 1) {
-      for (int p = t; p < n_pad / 2; p += 1024) {
+      for (int p = t; p < n_pad / 2; p += THREADS) {
         const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
         const int q = i | j;
         const uint64_t a = s[i], b = s[q];
@@ -490,9 +490,9 @@ __device__ void bitonic_sort_desc_1024(uint64_t* s) {
 
 // n_pad keys, 1024 threads: the register / shuffle form when the list fills the CTA, the plain form otherwise
 __device__ __forceinline__ void bitonic_sort_desc_cta(uint64_t* s, int n_pad) {
-  if (blockDim.x == 1024 && n_pad == 16384) bitonic_sort_desc_1024<16>(s);
-  else if (blockDim.x == 1024 && n_pad == 8192) bitonic_sort_desc_1024<8>(s);
-  else if (blockDim.x == 1024 && n_pad == 4096) bitonic_sort_desc_1024<4>(s);
+  if (blockDim.x == 1024 && n_pad == 16384) bitonic_sort_desc_regs<16, 1024>(s);
+  else if (blockDim.x == 1024 && n_pad == 8192) bitonic_sort_desc_regs<8, 1024>(s);
+  else if (blockDim.x == 1024 && n_pad == 4096) bitonic_sort_desc_regs<4, 1024>(s);
   else bitonic_sort_desc(s, n_pad);
 }
 
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(kRunLen / 2) run_sort_kernel(const uint32_t* _
   uint64_t* cand = cand_all + (size_t)f * N;
   for (int j = threadIdx.x; j < kRunLen; j += kRunLen / 2) s_key[j] = i0 + j < m ? cand[i0 + j] : 0ull;   // 0 < every key
   __syncthreads();
-  bitonic_sort_desc(s_key, kRunLen);
+  bitonic_sort_desc_regs<2, kRunLen / 2>(s_key);
   for (int j = threadIdx.x; j < kRunLen; j += kRunLen / 2)
     if (i0 + j < m) cand[i0 + j] = s_key[j];
 }
