@@ -72,7 +72,10 @@ class MultiScaleRoIAlign(nn.Module):
         return _MultiLevelFn.apply(rois, levels, self.output_size, tuple(self.scales), self.sampling_ratio, *feats)
 
 
-_FUSED_MAX_OUTPUTS = 1 << 23     # above this the per-level streaming kernels win (ops.roi_align dispatch)
+# One multi-level gather launch (no index lists, no host sync) up to this many outputs; the per-level streaming launches
+# (one nonzero() sync + one launch per level) are kept beyond it.  Measured on p2..p5 of Waymo frames, C = 256, 300 RoIs per
+# frame, crop stage per step: 4 frames 0.56 ms fused / 0.93 per level, 16 frames 2.07 / 2.7, 32 frames (120 M outputs) 3.26.
+_FUSED_MAX_OUTPUTS = 1 << 27
 
 
 class _MultiLevelFn(torch.autograd.Function):
