@@ -36,7 +36,9 @@ def med(fn, reps=20):
     return float(np.median(ts))
 
 
-fwd = med(lambda: ops._roi_align_forward(feat, sampled, (P, P), 1.0 / 16, 2, False))
-bwd = med(lambda: ops._roi_align_backward(grad_out, sampled, tuple(feat.shape), (P, P), 1.0 / 16, 2, False))
+seg = torch.full((F,), R, dtype=torch.int32, device=dev) if len(sys.argv) > 3 else None      # third argument: padded per-frame layout
+kw = dict(seg_count=seg, seg_stride=R) if seg is not None else {}
+fwd = med(lambda: ops._roi_align_forward(feat, sampled, (P, P), 1.0 / 16, 2, False, **kw))
+bwd = med(lambda: ops._roi_align_backward(grad_out, sampled, tuple(feat.shape), (P, P), 1.0 / 16, 2, False, **kw))
 alg_f = F * cfg["C"] * cfg["Hf"] * cfg["Wf"] * 4 + F * R * cfg["C"] * 49 * 4
-print(f"F={F} R={R}/frame: forward {fwd:.3f} ms ({alg_f / fwd / 1e6:.0f} GB/s), backward {bwd:.3f} ms ({alg_f / bwd / 1e6:.0f} GB/s)")
+print(f"F={F} R={R}/frame{' (segmented)' if seg is not None else ''}: forward {fwd:.3f} ms ({alg_f / fwd / 1e6:.0f} GB/s), backward {bwd:.3f} ms ({alg_f / bwd / 1e6:.0f} GB/s)")
