@@ -12,8 +12,6 @@
 //   C. ballot-free serial resolve over the alive bits (find-first-set walk)
 // and stops as soon as max_keep boxes are kept (post_nms_topN), which the reference's
 // keep[:post] slice makes equivalent.  Scratch traffic to HBM: none.
-#include <cstdio>
-
 #include "common.cuh"
 
 namespace b2d {
@@ -198,14 +196,6 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
   NmsClusterSmem& S = *reinterpret_cast<NmsClusterSmem*>(nms_smem_raw);
   pdl_trigger();
   pdl_wait();
-#ifdef B2D_AB_NMS_TIMING
-  unsigned long long tt[8];
-  int tn = 0;
-#define B2D_T() do { if (tn < 8) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[tn])); ++tn; } } while (0)
-#else
-#define B2D_T() do { } while (0)
-#endif
-  B2D_T();
   const int f = blockIdx.y;
   const uint32_t cta = cluster_ctarank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,7 +217,6 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
     for (int q = K_cached + tid; q < min(K, kKeptSmem); q += kNmsThreads) S.kept[q] = __ldcg(kept_boxes + q);
     K_cached = K;
     __syncthreads();
-    B2D_T();
     // ---- A: this CTA's 32 candidates, one warp each
     const int row = (int)cta * kRowsPerCta + warp;   // candidate within the chunk
     if (row < cn) {
@@ -259,9 +248,7 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
         if (lane < kChunkWords) st_cluster_u64(mask0 + (uint32_t)(row * kChunkWords + lane) * 8u, mine);
       }
     }
-    B2D_T();
     cluster_sync_all();
-    B2D_T();
     // ---- B: sweep (first warp of CTA 0)
     if (cta == 0 && warp == 0) {
       // lane w < 8: "removed" word of column tile w, seeded with the candidates the kept list already suppresses
@@ -274,15 +261,7 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
         if (lane == w) rem = ((unsigned long long)hi << 32) | lo;
       }
       int k = K;
-#ifdef B2D_AB_NMS_TIMING
-      unsigned long long s0, s1 = 0, s2 = 0;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(s0));
-#endif
       for (int t = 0; t < kChunkWords && k < max_keep; ++t) {
-#ifdef B2D_AB_NMS_TIMING
-        if (t == 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(s1));
-        if (t == 2) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(s2));
-#endif
         const int tile_n = min(64, cn - t * 64);
         if (tile_n <= 0) break;
         unsigned long long a = ~__shfl_sync(0xFFFFFFFFu, rem, t);       // undecided candidates of the tile
@@ -341,11 +320,7 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
         k += __popcll(kept_mask);
       }
       if (lane == 0) S.state[0] = k;
-#ifdef B2D_AB_NMS_TIMING
-      if (lane == 0 && base == 0) printf("  sweep: seed %llu, tile0 %llu, tile1 %llu ns, k=%d\n", s0 - tt[3], s1 - s0, s2 - s1, k);
-#endif
-      B2D_T();
-    }
+      }
     if (cta == 0) {
       __syncthreads();
       const int k1 = S.state[0];
@@ -361,14 +336,8 @@ nms_cluster_kernel(const float4* __restrict__ boxes_all, int n, const int32_t* _
       }
     }
     cluster_sync_all();
-    B2D_T();
     if (S.state[1]) break;
   }
-#ifdef B2D_AB_NMS_TIMING
-  if (cta == 0 && tid == 0)
-    printf("nms f=%d kept=%d nv=%d: start->loaded %llu, A %llu, sync %llu, sweep %llu, publish+sync %llu ns (first chunk)\n", f, S.state[0], nv,
-           tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], tt[5] - tt[4]);
-#endif
   if (cta == 0 && tid == 0) num_keep[f] = S.state[0];
 }
 

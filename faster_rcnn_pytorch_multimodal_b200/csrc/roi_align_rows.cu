@@ -105,10 +105,8 @@ __device__ unsigned long long g_ab_count[8];
 
 constexpr int kWarps = B2D_WARPS;          // 10 consumers + 2 producers (12 measured 1.2 % faster than 10: 35.8 vs 36.3 us/frame)
 constexpr int kThreads = kWarps * 32;
-#ifndef B2D_AB_CH
-#define B2D_AB_CH 32
-#endif
-constexpr int kCh = B2D_AB_CH;     // channels per CTA (lanes); the A/B value 16 only makes sense in the skeleton builds (fill cost of half-size rows)
+constexpr int kCh = 32;            // channels per CTA (lanes).  (16-channel CTAs, measured in a skeleton build: the fill protocol costs
+                                   // ~0.5 us per ROW whatever its size - 28.1 us per frame against 18.4)
 constexpr int kP = 7;              // PH = PW = 7
 constexpr int kRecVec = 32;        // float4 per item record
 constexpr int kRecBytes = kRecVec * 16;
