@@ -347,7 +347,13 @@ size_t nms_cluster_workspace_bytes(int F, int max_keep) {
 
 // 16-CTA clusters need the non-portable opt-in and a GPC with 16 free SMs: asked once per process.
 static bool cluster_nms_available() {
-  static const bool ok = [] {
+  // function attributes are per device: asked once per (thread, device)
+  static thread_local int cached_dev = -1;
+  static thread_local bool cached = false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev == cached_dev) return cached;
+  const bool ok = [] {
     if (cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
         cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(NmsClusterSmem)) != cudaSuccess) {
@@ -372,6 +378,8 @@ static bool cluster_nms_available() {
     }
     return n > 0;
   }();
+  cached_dev = dev;
+  cached = ok;
   return ok;
 }
 

@@ -194,3 +194,25 @@ def test_wrappers_switch_to_the_tensors_device():
     got = ops.roi_align(feat.to(dev(1)), rois.to(dev(1)), (7, 7), 1.0 / 16, 2, False)
     assert torch.allclose(got.cpu(), O.roi_align(feat, rois, (7, 7), 1.0 / 16, 2, False), rtol=1e-5, atol=1e-5)
     assert torch.cuda.current_device() == 0
+    # both devices from one process, one after the other: kernel attributes (cluster size, dynamic shared memory, the
+    # cooperative launch capacity) are per device
+    Hf, Wf, A = 24, 78, 25
+    gen = torch.Generator().manual_seed(10)
+    logits = torch.randn(2, Hf, Wf, 2 * A, generator=gen)
+    prob = torch.cat((logits[..., :A], logits[..., A:]), -1).sigmoid()
+    deltas = torch.randn(2, Hf, Wf, 4 * A, generator=gen) * 0.1
+    anchors = torch.from_numpy(O.generate_anchors_pre(Hf, Wf, 16, np.array([2, 4, 8, 16, 32]), np.array([0.5, 0.75, 1, 1.25, 2]), 1.0)[0])
+    info = torch.tensor([[0, 1242, 0, 375, 0, 0, 1.0]]).repeat(2, 1)
+    outs = []
+    for d in (0, 1, 0):
+        r, s, _, _, n = ops.proposal_batched(prob.to(dev(d)), deltas.to(dev(d)), info.to(dev(d)), anchors.to(dev(d)), None, A,
+                                             6000, 300, 0.7)
+        k, kn = ops.nms_sorted(r[:, :, 1:].contiguous(), 0.5)
+        k = k.cpu()
+        for f in range(2):
+            k[f, int(kn[f]):] = -1                     # (rows past the count are not written)
+        outs.append((r.cpu(), s.cpu(), n.cpu(), k, kn.cpu()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+    assert torch.cuda.current_device() == 0
